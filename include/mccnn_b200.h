@@ -1,0 +1,127 @@
+/*
+ * mccnn_b200.h -- C ABI of libmccnn_b200.so: the B200 (sm_100a) stereo-matching hot path of
+ * Jackie-Chou/MC-CNN-python, behind plain pointers and sizes.
+ *
+ * The reference has no FFI layer: its boundary is the module-level Python functions of
+ * src/process_functional.py ("pf") that src/match.py:132-175 calls.  Every entry point below
+ * replaces the BODY of one of those functions; the Python mirror in
+ * mc-cnn-python_b200/process_functional.py keeps the reference names and argument order and
+ * binds these symbols with ctypes.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in `_host`; float32 everywhere;
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*), allocates nothing,
+ *     keeps no global state except a thread-local error string, and returns 0 on success or a
+ *     negative mccnn_status; no C++ exception crosses the ABI;
+ *   - images      [H][W]          (the reference's [H,W,1] squeezed)
+ *   - features    [H][W][C]       (C = 64)
+ *   - disparity   [H][W]          float32 (the reference stores WTA indices as float32, pf:243)
+ *   - cost volume "HWD": [H][W][Dp], disparity fastest, Dp = mccnn_dpitch(D) = D rounded up to a
+ *     multiple of 4; the pad cells are never read as data.  The reference's logical [D,H,W]
+ *     array is the permuted view; mccnn_dhw_to_hwd / mccnn_hwd_to_dhw convert to and from the
+ *     reference's physical [D][H][W] order.
+ */
+#ifndef MCCNN_B200_H
+#define MCCNN_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum mccnn_status {
+    MCCNN_OK = 0,
+    MCCNN_ERR_ARG = -1,      /* invalid argument (message in mccnn_last_error) */
+    MCCNN_ERR_CUDA = -2,     /* a CUDA call or launch failed */
+    MCCNN_ERR_UNSUPPORTED = -3
+};
+
+/* Thread-local message of the last failing call ("" if none). */
+const char *mccnn_last_error(void);
+/* ABI version (bumped on any signature change). */
+int mccnn_abi_version(void);
+/* Physical disparity pitch of the HWD layout. */
+int mccnn_dpitch(int D);
+/* Number of kernels launched by this library in this process so far (for bench.py's gpu_launches). */
+unsigned long long mccnn_launch_count(void);
+
+/* [D][H][W] (reference order)  <->  [H][W][Dp] (this library's order). */
+int mccnn_dhw_to_hwd(const float *dhw, float *hwd, int D, int H, int W, void *stream);
+int mccnn_hwd_to_dhw(const float *hwd, float *dhw, int D, int H, int W, void *stream);
+
+/* ---- a1/a2  model.NET forward + pf:15 compute_features (model.py:40-64, :90-125; pf:20-25) ----
+ * img [H][W] normalised image with `pad` implicit zero pixels per side (compute_features pads by
+ * (patch-1)/2 = num_layers, pf:20-25; NET itself applies VALID convolutions, pad = 0).
+ * weights_host / biases_host: HOST arrays of num_layers DEVICE pointers; weights HWIO
+ * ([3][3][1][64], then [3][3][64][64]), biases [64].
+ * out [H+2pad-2n][W+2pad-2n][64], L2-normalised over channels (model.py:64).
+ * scratch: mccnn_features_scratch_bytes(H, W, pad, num_layers) bytes. */
+size_t mccnn_features_scratch_bytes(int H, int W, int pad, int num_layers);
+int mccnn_features(const float *img, int H, int W, int pad, int num_layers,
+                   const float *const *weights_host, const float *const *biases_host,
+                   float *out, void *scratch, void *stream);
+
+/* ---- a3  pf:78 compute_cost_volume ----
+ * fl, fr [H][W][C]; L, R: HWD volumes.  Requires C == 64, D >= 1, W >= D + 2. */
+int mccnn_cost_volume(const float *fl, const float *fr, float *L, float *R,
+                      int H, int W, int C, int D, void *stream);
+
+/* ---- a4  pf:571 compute_cross_region, arm-length form ----
+ * arms [H][W][4] u8 = {up, down, left, right}; count [H][W] i32 = |U(h,w)|. */
+int mccnn_cross_arms(const float *img, uint8_t *arms, int32_t *count, int H, int W,
+                     float intensity_threshold, int distance_threshold, void *stream);
+/* The reference's explicit list: region [H][W][(2*dist)^2][2] i32 padded with -1 (pf:638-655). */
+int mccnn_cross_region_list(const uint8_t *arms, int32_t *region, int H, int W,
+                            int distance_threshold, void *stream);
+
+/* ---- a5  pf:117 cost_volume_aggregation, one volume ----
+ * `iters` rounds of region mean; in is left untouched, out receives the result, scratch is one
+ * more HWD volume.  Flat float32 running sum in the reference's enumeration order (pf:149-163). */
+int mccnn_cbca(const float *in, float *out, float *scratch, const uint8_t *arms,
+               const int32_t *count, int D, int H, int W, int iters, void *stream);
+
+/* ---- a6  pf:476 semi_global_matching, one in-place pass over one volume ----
+ * (rh, rw) in {(0,1),(0,-1),(-1,0),(1,0)}.  P1/P2/Q1/Q2/tauD arrive as doubles and are rounded to
+ * float32 exactly where the reference rounds them (pf:504-505, :538-541).
+ * flags_scratch: mccnn_sgm_scratch_bytes(H, W, D) bytes. */
+size_t mccnn_sgm_scratch_bytes(int H, int W, int D);
+int mccnn_sgm_pass(float *vol, const float *img_left, const float *img_right, void *flags_scratch,
+                   int D, int H, int W, int rh, int rw,
+                   double sgm_P1, double sgm_P2, double sgm_Q1, double sgm_Q2, double sgm_D,
+                   int is_left, void *stream);
+/* ---- a7  pf:187 SGM_average for one volume: the four chained in-place passes (pf:194-210). */
+int mccnn_sgm_average(float *vol, const float *img_left, const float *img_right, void *flags_scratch,
+                      int D, int H, int W,
+                      double sgm_P1, double sgm_P2, double sgm_Q1, double sgm_Q2, double sgm_D,
+                      double sgm_V, int is_left, void *stream);
+
+/* Both volumes of a pair in shared launches (the two volumes are independent until WTA); either
+ * volume pointer may be NULL. */
+int mccnn_sgm_average_pair(float *vol_left, float *vol_right, const float *img_left, const float *img_right,
+                           void *flags_scratch, int D, int H, int W,
+                           double sgm_P1, double sgm_P2, double sgm_Q1, double sgm_Q2, double sgm_D,
+                           double sgm_V, void *stream);
+
+/* ---- a8  pf:239 disparity_prediction, one volume: first minimum over d, stored as float32. */
+int mccnn_wta(const float *vol, float *disp, int D, int H, int W, void *stream);
+
+/* ---- a9  pf:279 interpolation.  labels [H][W] i32 scratch/output (0 match, 1 mismatch, 2 occlusion). */
+int mccnn_lr_interp(const float *disp_left, const float *disp_right, float *out, int32_t *labels,
+                    int H, int W, int ndisp, void *stream);
+
+/* ---- a10 pf:381 subpixel_enhance (vol is the HWD left volume). */
+int mccnn_subpixel(const float *disp, const float *vol, float *out, int D, int H, int W, void *stream);
+
+/* ---- a11 pf:403 median_filter: border-clipped fh x fw window, np.median semantics; fh*fw <= 121. */
+int mccnn_median(const float *in, float *out, int H, int W, int fh, int fw, void *stream);
+
+/* ---- a12 pf:424 bilateral_filter.  table [fh][fw] = float32 weights of pf:433-436; fh*fw <= 121. */
+int mccnn_bilateral(const float *img, const float *in, float *out, const float *table,
+                    int H, int W, int fh, int fw, float blur_threshold, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MCCNN_B200_H */

@@ -1,0 +1,164 @@
+// Cross-based cost aggregation (pf:117-183, pf:571-657).  Compiled with -fmad=false.
+//
+// Support regions are kept as four arm lengths per pixel (4 B) instead of the reference's
+// explicit coordinate list (6.3 KB per pixel, pf:638); |U| is a precomputed int32.
+// The aggregation walks the region in the reference's own enumeration order (pf:640-650) with one
+// float32 running sum per cell (pf:157-161), so the result is bit-identical to the reference.
+// HWD layout makes that walk cheap: the lanes of a warp are the disparities of one or two
+// pixels, so every lane follows the same arms (no divergence) and every load is a contiguous
+// 16 B granule of the neighbour pixel's disparity row (fully coalesced for any region shape).
+#include "common.cuh"
+
+namespace mccnn {
+
+// a4: arms.  One thread per pixel; each arm stops at the first neighbour whose intensity differs
+// from the ANCHOR by >= tau (pf:588, :596, :615, :623) or after dist-1 pixels.
+__global__ void k_cross_arms(const float *__restrict__ img, uchar4 *__restrict__ arms, int H, int W, float tau,
+                             int dist) {
+    int w = blockIdx.x * blockDim.x + threadIdx.x;
+    int h = blockIdx.y * blockDim.y + threadIdx.y;
+    if (w >= W || h >= H) return;
+    const float cur = img[(size_t)h * W + w];
+    int up = 0, down = 0, left = 0, right = 0, lim;
+    lim = min(dist, h + 1);                                              // pf:585
+    for (int b = 1; b < lim; b++) { if (fabsf(cur - img[(size_t)(h - b) * W + w]) >= tau) break; up = b; }
+    lim = min(dist, H - h);                                              // pf:593
+    for (int b = 1; b < lim; b++) { if (fabsf(cur - img[(size_t)(h + b) * W + w]) >= tau) break; down = b; }
+    lim = min(dist, w + 1);                                              // pf:612
+    for (int b = 1; b < lim; b++) { if (fabsf(cur - img[(size_t)h * W + w - b]) >= tau) break; left = b; }
+    lim = min(dist, W - w);                                              // pf:620
+    for (int b = 1; b < lim; b++) { if (fabsf(cur - img[(size_t)h * W + w + b]) >= tau) break; right = b; }
+    arms[(size_t)h * W + w] = make_uchar4((unsigned char)up, (unsigned char)down, (unsigned char)left,
+                                          (unsigned char)right);
+}
+
+// |U(h,w)| = sum over the vertical arm of (left + right + 1) of each spine pixel (pf:640-652).
+__global__ void k_cross_count(const uchar4 *__restrict__ arms, int32_t *__restrict__ count, int H, int W) {
+    int w = blockIdx.x * blockDim.x + threadIdx.x;
+    int h = blockIdx.y * blockDim.y + threadIdx.y;
+    if (w >= W || h >= H) return;
+    uchar4 a = arms[(size_t)h * W + w];
+    int n = 0;
+    for (int hh = h - a.x; hh <= h + a.y; hh++) {
+        uchar4 s = arms[(size_t)hh * W + w];
+        n += s.z + s.w + 1;
+    }
+    count[(size_t)h * W + w] = n;
+}
+
+// Compatibility view: the reference's explicit list, in its own order (pf:640-655).
+__global__ void k_cross_region_list(const uchar4 *__restrict__ arms, int32_t *__restrict__ region, int H, int W,
+                                    int max_num) {
+    int w = blockIdx.x * blockDim.x + threadIdx.x;
+    int h = blockIdx.y * blockDim.y + threadIdx.y;
+    if (w >= W || h >= H) return;
+    int2 *out = reinterpret_cast<int2 *>(region) + ((size_t)h * W + w) * max_num;
+    uchar4 a = arms[(size_t)h * W + w];
+    int n = 0;
+    for (int k = 0; k <= a.x + a.y; k++) {
+        int hh = (k <= a.x) ? h - k : h + (k - a.x);
+        uchar4 s = arms[(size_t)hh * W + w];
+        for (int j = 0; j <= s.z + s.w; j++) {
+            int ww = (j <= s.z) ? w - j : w + (j - s.z);
+            out[n++] = make_int2(hh, ww);
+        }
+    }
+    for (; n < max_num; n++) out[n] = make_int2(-1, -1);
+}
+
+// a5: one aggregation round.  A block owns a TH x TW pixel tile (so neighbouring regions share
+// L1 lines); its threads stride over (pixel, granule) items; one item = 4 disparities of one pixel.
+constexpr int CBCA_TH = 8, CBCA_TW = 16, CBCA_THREADS = 256;
+
+__global__ void __launch_bounds__(CBCA_THREADS) k_cbca_round(const float4 *__restrict__ in, float4 *__restrict__ out,
+                                                             const uchar4 *__restrict__ arms,
+                                                             const int32_t *__restrict__ count, int G, int H, int W) {
+    const int h0 = blockIdx.y * CBCA_TH, w0 = blockIdx.x * CBCA_TW;
+    const int items = CBCA_TH * CBCA_TW * G;
+    for (int item = threadIdx.x; item < items; item += CBCA_THREADS) {
+        const int px = item / G, g = item - px * G;
+        const int h = h0 + px / CBCA_TW, w = w0 + px % CBCA_TW;
+        if (h >= H || w >= W) continue;
+        const size_t p = (size_t)h * W + w;
+        const uchar4 a = arms[p];
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);                    // pf:157
+        const int nrows = a.x + a.y;
+        for (int k = 0; k <= nrows; k++) {
+            const int hh = (k <= a.x) ? h - k : h + (k - a.x);            // spine order h, h-1.., h+1..
+            const size_t rowp = (size_t)hh * W;
+            const uchar4 s = arms[rowp + w];
+            const float4 *src = in + (rowp + w) * G + g;
+            // w, w-1, ..., w-left
+            for (int j = 0; j <= s.z; j++) {
+                float4 v = src[-(ptrdiff_t)j * G];
+                acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;  // pf:160
+            }
+            // w+1, ..., w+right
+            for (int j = 1; j <= s.w; j++) {
+                float4 v = src[(ptrdiff_t)j * G];
+                acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+            }
+        }
+        const float n = (float)count[p];
+        out[p * G + g] = make_float4(acc.x / n, acc.y / n, acc.z / n, acc.w / n);   // pf:161
+    }
+}
+
+}  // namespace mccnn
+
+using namespace mccnn;
+
+extern "C" {
+
+int mccnn_cross_arms(const float *img, uint8_t *arms, int32_t *count, int H, int W, float tau, int dist,
+                     void *stream) {
+    MCCNN_REQUIRE(img && arms && count && H >= 1 && W >= 1, "cross_arms: bad arguments");
+    MCCNN_REQUIRE(dist >= 1 && dist <= 255, "cross_arms: distance_threshold %d outside [1, 255]", dist);
+    MCCNN_REQUIRE(tau > 0.0f, "cross_arms: intensity_threshold must be > 0 (asserts at pf:601, :628)");
+    cudaStream_t s = (cudaStream_t)stream;
+    dim3 block(32, 8), grid(cdiv(W, 32), cdiv(H, 8));
+    k_cross_arms<<<grid, block, 0, s>>>(img, reinterpret_cast<uchar4 *>(arms), H, W, tau, dist);
+    MCCNN_LAUNCHED("cross_arms");
+    k_cross_count<<<grid, block, 0, s>>>(reinterpret_cast<const uchar4 *>(arms), count, H, W);
+    MCCNN_LAUNCHED("cross_count");
+    return MCCNN_OK;
+}
+
+int mccnn_cross_region_list(const uint8_t *arms, int32_t *region, int H, int W, int dist, void *stream) {
+    MCCNN_REQUIRE(arms && region && H >= 1 && W >= 1 && dist >= 1 && dist <= 255, "cross_region_list: bad arguments");
+    dim3 block(32, 8), grid(cdiv(W, 32), cdiv(H, 8));
+    k_cross_region_list<<<grid, block, 0, (cudaStream_t)stream>>>(reinterpret_cast<const uchar4 *>(arms), region, H, W,
+                                                                  (2 * dist) * (2 * dist));
+    MCCNN_LAUNCHED("cross_region_list");
+    return MCCNN_OK;
+}
+
+int mccnn_cbca(const float *in, float *out, float *scratch, const uint8_t *arms, const int32_t *count, int D, int H,
+               int W, int iters, void *stream) {
+    MCCNN_REQUIRE(in && out && arms && count && D >= 1 && H >= 1 && W >= 1 && iters >= 0, "cbca: bad arguments");
+    MCCNN_REQUIRE(in != out, "cbca: in and out must differ (the reference leaves its input untouched, pf:119)");
+    MCCNN_REQUIRE(iters < 2 || (scratch && scratch != in && scratch != out), "cbca: scratch volume required for iters >= 2");
+    cudaStream_t s = (cudaStream_t)stream;
+    const int Dp = dpitch(D), G = Dp / 4;
+    if (iters == 0) {
+        MCCNN_CUDA(cudaMemcpyAsync(out, in, (size_t)H * W * Dp * sizeof(float), cudaMemcpyDeviceToDevice, s));
+        return MCCNN_OK;
+    }
+    dim3 grid(cdiv(W, CBCA_TW), cdiv(H, CBCA_TH));
+    // ping-pong so that the last round lands in `out`
+    float *buf[2];
+    buf[(iters - 1) & 1] = out;
+    buf[iters & 1] = scratch;
+    const float *src = in;
+    for (int it = 0; it < iters; it++) {
+        float *dst = buf[it & 1];
+        k_cbca_round<<<grid, CBCA_THREADS, 0, s>>>(reinterpret_cast<const float4 *>(src),
+                                                    reinterpret_cast<float4 *>(dst),
+                                                    reinterpret_cast<const uchar4 *>(arms), count, G, H, W);
+        MCCNN_LAUNCHED("cbca_round");
+        src = dst;
+    }
+    return MCCNN_OK;
+}
+
+}  // extern "C"

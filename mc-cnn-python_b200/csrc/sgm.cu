@@ -1,0 +1,317 @@
+// Semi-global matching (pf:476-568, pf:187-235).  Compiled with -fmad=false; bit-exact against the
+// reference: only +, -, min and four pre-divided penalty constants are involved, evaluated in the
+// reference's order ((C + min(...)) - m, pf:552/559/566).
+//
+// Mapping: one warp per scanline, lanes over disparity.  In the HWD layout the D-vector of a pixel
+// is contiguous, so every step of every direction reads and writes one coalesced 4*Dp-byte run;
+// the four directions are the same kernel with a different pixel stride.  Lane l owns the float4
+// granules g = l + NLg*j (j < JP), the previous pixel's path costs stay in registers, neighbours
+// d-1 / d+1 that cross a granule come from two warp shuffles per granule, and the minimum over D
+// is one redux.sync on an order-preserving integer key.  The input cells of the next PF steps are
+// prefetched into a register ring so that the HBM latency is off the recurrence's critical path.
+//
+// Image-adaptive penalties (pf:504-541) are not materialised as [D,H,W] arrays: the two gradient
+// tests D1 >= tauD / D2 >= tauD are precomputed once per pass as bit maps of the two images
+// (k_sgm_flags) and looked up per cell.
+#include "common.cuh"
+#include <math_constants.h>
+
+namespace mccnn {
+
+struct SgmJob {
+    float *vol;
+    const uint32_t *own_map;   // gradient-flag bit map of the volume's own image (eh or ev)
+    const uint32_t *oth_map;   // ... of the other image
+    int is_left;
+};
+
+struct SgmParams {
+    SgmJob job[2];
+    int D, G, NLg, H, W, WR, PADW;
+    int rh, rw;
+    float P1, P2, P1q1, P2q1, P1q2, P2q2;
+};
+
+// Bit maps.  eh(h,x) = x>=1 && |I(h,x)-I(h,x-1)| >= tauD ; ev(h,x) = h>=1 && |I(h,x)-I(h-1,x)| >= tauD.
+// Rows are padded with PADW zero words on both sides so that x = w -/+ d outside the image reads 0,
+// which is the reference's "D2 = 0 when the correspondent is outside" (pf:516-520, :529-533).
+// maps: [image(2)][kind(2: eh, ev)][H][WR] u32.
+__global__ void k_sgm_flags(const float *__restrict__ img0, const float *__restrict__ img1, uint32_t *__restrict__ maps,
+                            int H, int W, int WR, int PADW, float tauD) {
+    const int pos = blockIdx.x * blockDim.x + threadIdx.x;      // bit position within the padded row
+    const int h = blockIdx.y;
+    const float *img = blockIdx.z ? img1 : img0;
+    const int x = pos - PADW * 32;
+    bool fh = false, fv = false;
+    if (x >= 0 && x < W) {
+        float c = img[(size_t)h * W + x];
+        if (x >= 1) fh = fabsf(c - img[(size_t)h * W + x - 1]) >= tauD;
+        if (h >= 1) fv = fabsf(c - img[(size_t)(h - 1) * W + x]) >= tauD;
+    }
+    unsigned bh = __ballot_sync(0xffffffffu, fh), bv = __ballot_sync(0xffffffffu, fv);
+    const int word = pos >> 5;
+    if ((threadIdx.x & 31) == 0 && word < WR) {
+        size_t base = ((size_t)blockIdx.z * 2) * H * WR;
+        maps[base + (size_t)h * WR + word] = bh;
+        maps[base + (size_t)H * WR + (size_t)h * WR + word] = bv;
+    }
+}
+
+__device__ __forceinline__ int f2key(float x) {
+    int i = __float_as_int(x);
+    return i ^ ((i >> 31) & 0x7fffffff);
+}
+__device__ __forceinline__ float key2f(int k) { return __int_as_float(k ^ ((k >> 31) & 0x7fffffff)); }
+
+template <int JP, int PF>
+__global__ void __launch_bounds__(32, 16) k_sgm_pass(const __grid_constant__ SgmParams prm) {
+    const SgmJob job = prm.job[blockIdx.y];
+    const int lane = threadIdx.x;
+    const int line = blockIdx.x;
+    const int G = prm.G, NLg = prm.NLg, W = prm.W, H = prm.H, D = prm.D, WR = prm.WR;
+    const bool horizontal = (prm.rh == 0);
+    const int N = horizontal ? W : H;
+    int h0, w0, dh, dw;
+    if (horizontal) { h0 = line; dh = 0; dw = prm.rw; w0 = prm.rw > 0 ? 0 : W - 1; }
+    else            { w0 = line; dw = 0; dh = prm.rh; h0 = prm.rh > 0 ? 0 : H - 1; }
+    const int hoff = prm.rh < 0 ? 1 : 0, woff = prm.rw < 0 ? 1 : 0;
+    const long long pstride = (long long)dh * W + dw;            // pixels per step
+    const long long p0 = (long long)h0 * W + w0;
+    float4 *const vol4 = reinterpret_cast<float4 *>(job.vol);
+    const float INF = CUDART_INF_F;
+
+    int g[JP];
+    bool gv[JP];
+#pragma unroll
+    for (int j = 0; j < JP; j++) { g[j] = lane + NLg * j; gv[j] = (lane < NLg) && (g[j] < G); }
+    const bool ragged = (D & 3) != 0;
+    const int src_dn = (lane == 0) ? NLg - 1 : lane - 1;
+    const int src_up = (lane >= NLg - 1) ? 0 : lane + 1;
+    const bool first_lane = (lane == 0), last_lane = (lane == NLg - 1);
+
+    auto load_cells = [&](int t, float4 (&dst)[JP]) {
+        const long long p = p0 + (long long)t * pstride;
+#pragma unroll
+        for (int j = 0; j < JP; j++) {
+            float4 v = make_float4(INF, INF, INF, INF);
+            if (gv[j]) {
+                v = vol4[p * G + g[j]];
+                if (ragged) {
+                    int d = g[j] << 2;
+                    if (d + 1 >= D) v.y = INF;
+                    if (d + 2 >= D) v.z = INF;
+                    if (d + 3 >= D) v.w = INF;
+                }
+            }
+            dst[j] = v;
+        }
+    };
+    // 4-bit penalty selectors of this lane's granules at step t (bit k <-> d = 4g + k), own flag in bit 31
+    auto load_flags = [&](int t, uint32_t (&dst)[JP], uint32_t &own) {
+        const int hb = h0 + t * dh + hoff, wb = w0 + t * dw + woff;
+        const uint32_t *orow = job.oth_map + (size_t)hb * WR;
+        const int pos1 = prm.PADW * 32 + wb;
+        own = (job.own_map[(size_t)hb * WR + (pos1 >> 5)] >> (pos1 & 31)) & 1u;
+#pragma unroll
+        for (int j = 0; j < JP; j++) {
+            uint32_t f = 0;
+            if (gv[j]) {
+                if (job.is_left) {
+                    int pos = pos1 - 4 * g[j] - 3;                 // x = wb - d, d = 4g+3 .. 4g
+                    f = __funnelshift_r(orow[pos >> 5], orow[(pos >> 5) + 1], pos & 31) & 15u;
+                    f = __brev(f) >> 28;
+                } else {
+                    int pos = pos1 + 4 * g[j];                     // x = wb + d
+                    f = __funnelshift_r(orow[pos >> 5], orow[(pos >> 5) + 1], pos & 31) & 15u;
+                }
+            }
+            dst[j] = f;
+        }
+    };
+
+    // step 0: the first pixel of the scanline is left unchanged (pf:485-501) and seeds the recurrence
+    float4 prev[JP];
+    load_cells(0, prev);
+    float m;
+    {
+        float lm = INF;
+#pragma unroll
+        for (int j = 0; j < JP; j++) lm = fminf(fminf(lm, fminf(prev[j].x, prev[j].y)), fminf(prev[j].z, prev[j].w));
+        m = key2f(__reduce_min_sync(0xffffffffu, f2key(lm)));
+    }
+
+    float4 ring[PF][JP];
+    uint32_t fring[PF][JP];
+    uint32_t oring[PF];
+#pragma unroll
+    for (int u = 0; u < PF; u++)
+        if (1 + u < N) { load_cells(1 + u, ring[u]); load_flags(1 + u, fring[u], oring[u]); }
+
+    for (int t0 = 1; t0 < N; t0 += PF) {
+#pragma unroll
+        for (int u = 0; u < PF; u++) {
+            const int t = t0 + u;
+            if (t < N) {                                           // warp-uniform
+                float4 cur[JP];
+                uint32_t fb[JP];
+#pragma unroll
+                for (int j = 0; j < JP; j++) { cur[j] = ring[u][j]; fb[j] = fring[u][j]; }
+                const uint32_t f1 = oring[u];
+                if (t + PF < N) { load_cells(t + PF, ring[u]); load_flags(t + PF, fring[u], oring[u]); }
+
+                // penalties (pf:535-541): f1 = (D1 >= tauD), per-cell bit = (D2 >= tauD)
+                const float pa1 = f1 ? prm.P1q1 : prm.P1, pb1 = f1 ? prm.P1q2 : prm.P1q1;
+                const float cA = m + (f1 ? prm.P2q1 : prm.P2), cB = m + (f1 ? prm.P2q2 : prm.P2q1);
+                float rw_[JP], rx_[JP];
+#pragma unroll
+                for (int j = 0; j < JP; j++) {
+                    rw_[j] = __shfl_sync(0xffffffffu, prev[j].w, src_dn);
+                    rx_[j] = __shfl_sync(0xffffffffu, prev[j].x, src_up);
+                }
+                float lm = INF;
+                const long long p = p0 + (long long)t * pstride;
+#pragma unroll
+                for (int j = 0; j < JP; j++) {
+                    const float lnb = first_lane ? (j > 0 ? rw_[j > 0 ? j - 1 : 0] : INF) : rw_[j];
+                    const float rnb = last_lane ? (j < JP - 1 ? rx_[j < JP - 1 ? j + 1 : 0] : INF) : rx_[j];
+                    const float4 q = prev[j];
+                    const uint32_t b = fb[j];
+                    float4 o;
+                    o.x = (cur[j].x + fminf(q.x, fminf(fminf(lnb, q.y) + ((b & 1u) ? pb1 : pa1), (b & 1u) ? cB : cA))) - m;
+                    o.y = (cur[j].y + fminf(q.y, fminf(fminf(q.x, q.z) + ((b & 2u) ? pb1 : pa1), (b & 2u) ? cB : cA))) - m;
+                    o.z = (cur[j].z + fminf(q.z, fminf(fminf(q.y, q.w) + ((b & 4u) ? pb1 : pa1), (b & 4u) ? cB : cA))) - m;
+                    o.w = (cur[j].w + fminf(q.w, fminf(fminf(q.z, rnb) + ((b & 8u) ? pb1 : pa1), (b & 8u) ? cB : cA))) - m;
+                    if (gv[j]) vol4[p * G + g[j]] = o;
+                    prev[j] = o;
+                    lm = fminf(fminf(lm, fminf(o.x, o.y)), fminf(o.z, o.w));
+                }
+                m = key2f(__reduce_min_sync(0xffffffffu, f2key(lm)));
+            }
+        }
+    }
+}
+
+static int launch_pass(const SgmParams &prm, int njobs, cudaStream_t s) {
+    const int JP = cdiv(prm.G, 32);
+    const bool horizontal = (prm.rh == 0);
+    dim3 grid(horizontal ? prm.H : prm.W, njobs), block(32);
+    switch (JP) {
+        case 1: k_sgm_pass<1, 6><<<grid, block, 0, s>>>(prm); break;
+        case 2: k_sgm_pass<2, 4><<<grid, block, 0, s>>>(prm); break;
+        case 3: k_sgm_pass<3, 3><<<grid, block, 0, s>>>(prm); break;
+        case 4: k_sgm_pass<4, 2><<<grid, block, 0, s>>>(prm); break;
+        default:
+            set_error("sgm: ndisp %d too large (max 512)", prm.D);
+            return MCCNN_ERR_UNSUPPORTED;
+    }
+    return check_launch("sgm_pass");
+}
+
+struct SgmGeom { int WR, PADW; size_t map_words; };
+static SgmGeom sgm_geom(int H, int W, int D) {
+    SgmGeom g;
+    g.PADW = cdiv(dpitch(D), 32) + 1;
+    g.WR = 2 * g.PADW + cdiv(W, 32) + 1;
+    g.map_words = (size_t)H * g.WR;
+    return g;
+}
+
+static int build_flags(const float *img_left, const float *img_right, uint32_t *maps, int H, int W, int D, float tauD,
+                       cudaStream_t s) {
+    SgmGeom gm = sgm_geom(H, W, D);
+    dim3 block(256), grid(cdiv((long long)gm.WR * 32, 256), H, 2);
+    k_sgm_flags<<<grid, block, 0, s>>>(img_left, img_right, maps, H, W, gm.WR, gm.PADW, tauD);
+    return check_launch("sgm_flags");
+}
+
+static int check_dir(int rh, int rw) {
+    return (rh == 0 && (rw == 1 || rw == -1)) || (rw == 0 && (rh == 1 || rh == -1));
+}
+
+static void fill_params(SgmParams &prm, int D, int H, int W, int rh, int rw, double P1, double P2, double Q1, double Q2) {
+    SgmGeom gm = sgm_geom(H, W, D);
+    prm.D = D; prm.G = dpitch(D) / 4; prm.H = H; prm.W = W; prm.WR = gm.WR; prm.PADW = gm.PADW;
+    prm.NLg = cdiv(prm.G, cdiv(prm.G, 32));
+    prm.rh = rh; prm.rw = rw;
+    // float32 rounding exactly as pf:504-505 (P*ones(float32)) and pf:538-541 (float32 array / scalar)
+    const float P1a = (float)P1, P2a = (float)P2, q1 = (float)Q1, q2 = (float)Q2;
+    prm.P1 = P1a; prm.P2 = P2a;
+    prm.P1q1 = P1a / q1; prm.P2q1 = P2a / q1; prm.P1q2 = P1a / q2; prm.P2q2 = P2a / q2;
+}
+
+static void fill_job(SgmJob &job, float *vol, uint32_t *maps, int H, int W, int D, int rh, int is_left) {
+    SgmGeom gm = sgm_geom(H, W, D);
+    const int kind = (rh == 0) ? 0 : 1;                       // eh for horizontal passes, ev for vertical
+    const uint32_t *left = maps + (size_t)(0 * 2 + kind) * gm.map_words;
+    const uint32_t *right = maps + (size_t)(1 * 2 + kind) * gm.map_words;
+    job.vol = vol;
+    job.is_left = is_left;
+    job.own_map = is_left ? left : right;
+    job.oth_map = is_left ? right : left;
+}
+
+}  // namespace mccnn
+
+using namespace mccnn;
+
+extern "C" {
+
+size_t mccnn_sgm_scratch_bytes(int H, int W, int D) {
+    if (H < 1 || W < 1 || D < 1) return 0;
+    return 4 * sgm_geom(H, W, D).map_words * sizeof(uint32_t);
+}
+
+int mccnn_sgm_pass(float *vol, const float *img_left, const float *img_right, void *flags_scratch, int D, int H, int W,
+                   int rh, int rw, double P1, double P2, double Q1, double Q2, double tauD, int is_left, void *stream) {
+    MCCNN_REQUIRE(vol && img_left && img_right && flags_scratch, "sgm_pass: null pointer");
+    MCCNN_REQUIRE(D >= 2 && H >= 1 && W >= 1, "sgm_pass: need ndisp >= 2 (pf:547-566), got D=%d H=%d W=%d", D, H, W);
+    MCCNN_REQUIRE(check_dir(rh, rw), "sgm_pass: direction (%d,%d) is not axis-aligned (pf:484)", rh, rw);
+    MCCNN_REQUIRE(tauD > 0.0, "sgm_pass: sgm_D must be > 0");
+    cudaStream_t s = (cudaStream_t)stream;
+    uint32_t *maps = (uint32_t *)flags_scratch;
+    int rc = build_flags(img_left, img_right, maps, H, W, D, (float)tauD, s);
+    if (rc) return rc;
+    SgmParams prm;
+    fill_params(prm, D, H, W, rh, rw, P1, P2, Q1, Q2);
+    fill_job(prm.job[0], vol, maps, H, W, D, rh, is_left);
+    prm.job[1] = prm.job[0];
+    return launch_pass(prm, 1, s);
+}
+
+// Both volumes of a pair, four chained passes each (pf:194-208 and :212-230).  The final
+// (X+X+X+X)/4. of pf:210/:232 is the identity on finite float32 and is not executed.
+// vol_right may be NULL (left volume only) and vice versa.
+int mccnn_sgm_average_pair(float *vol_left, float *vol_right, const float *img_left, const float *img_right,
+                           void *flags_scratch, int D, int H, int W, double P1, double P2, double Q1, double Q2,
+                           double tauD, double V, void *stream) {
+    MCCNN_REQUIRE((vol_left || vol_right) && img_left && img_right && flags_scratch, "sgm_average: null pointer");
+    MCCNN_REQUIRE(D >= 2 && H >= 1 && W >= 1, "sgm_average: need ndisp >= 2, got D=%d H=%d W=%d", D, H, W);
+    MCCNN_REQUIRE(tauD > 0.0 && V != 0.0, "sgm_average: sgm_D must be > 0 and sgm_V non-zero");
+    cudaStream_t s = (cudaStream_t)stream;
+    uint32_t *maps = (uint32_t *)flags_scratch;
+    int rc = build_flags(img_left, img_right, maps, H, W, D, (float)tauD, s);
+    if (rc) return rc;
+    const int dirs[4][2] = {{0, 1}, {0, -1}, {-1, 0}, {1, 0}};      // pf:195, :198, :203, :207
+    for (int i = 0; i < 4; i++) {
+        const int rh = dirs[i][0], rw = dirs[i][1];
+        SgmParams prm;
+        // vertical passes use P1/V formed in float64 by the caller (pf:204), then rounded to float32
+        fill_params(prm, D, H, W, rh, rw, rh == 0 ? P1 : P1 / V, P2, Q1, Q2);
+        int n = 0;
+        if (vol_left) fill_job(prm.job[n++], vol_left, maps, H, W, D, rh, 1);
+        if (vol_right) fill_job(prm.job[n++], vol_right, maps, H, W, D, rh, 0);
+        if (n == 1) prm.job[1] = prm.job[0];
+        rc = launch_pass(prm, n, s);
+        if (rc) return rc;
+    }
+    return MCCNN_OK;
+}
+
+int mccnn_sgm_average(float *vol, const float *img_left, const float *img_right, void *flags_scratch, int D, int H,
+                      int W, double P1, double P2, double Q1, double Q2, double tauD, double V, int is_left,
+                      void *stream) {
+    return mccnn_sgm_average_pair(is_left ? vol : nullptr, is_left ? nullptr : vol, img_left, img_right, flags_scratch, D,
+                                  H, W, P1, P2, Q1, Q2, tauD, V, stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,229 @@
+"""The body of the reference's per-pair loop (match.py:131-175) as one reusable object.
+
+``StereoMatcher`` owns every device buffer a pair of shape (H, W, ndisp) needs (allocated once
+with torch), and ``run`` issues the hot path -- features, cost volume, CBCA x iters1, four chained
+SGM passes, CBCA x iters2, WTA, LR-check/interpolation, sub-pixel, median, bilateral -- as a fixed
+sequence of C-ABI calls on the current CUDA stream: no allocation, no host synchronisation and no
+host<->device traffic inside.  ``run_host`` is the same with NumPy images in / NumPy disparity out
+through pinned staging buffers (what match.py's loop body amounts to end to end).
+
+Hyper-parameter defaults are match.py:32-43.
+"""
+import ctypes
+
+import numpy as np
+
+try:
+    from . import _ffi
+    from . import process_functional as _pf
+except ImportError:
+    import _ffi
+    import process_functional as _pf
+
+DEFAULTS = dict(patch_size=11, cbca_intensity=0.02, cbca_distance=14, cbca_num_iterations1=2,
+                cbca_num_iterations2=16, sgm_P1=2.3, sgm_P2=55.9, sgm_Q1=4, sgm_Q2=8, sgm_D=0.08, sgm_V=1.5,
+                blur_sigma=6, blur_threshold=2)
+
+STAGES = ("features", "cost_volume", "cbca1", "sgm", "cbca2", "wta", "interpolation", "subpixel", "median",
+          "bilateral")
+
+
+class StereoMatcher(object):
+
+    def __init__(self, H, W, ndisp, checkpoint=None, stages=STAGES, **hp):
+        torch = _pf._torch()
+        self.torch = torch
+        self.H, self.W, self.D = int(H), int(W), int(ndisp)
+        self.hp = dict(DEFAULTS)
+        self.hp.update(hp)
+        self.stages = tuple(stages)
+        for s in self.stages:
+            assert s in STAGES, "unknown stage %r" % s
+        H, W, D = self.H, self.W, self.D
+        assert D >= 2 and W >= D + 2, "need ndisp >= 2 and W >= ndisp + 2 (pf:94-95, :547-566)"
+        dev = _pf._dev()
+        self.device = dev
+        f32 = torch.float32
+        self.pad = (int(self.hp["patch_size"]) - 1) // 2
+        self.weights = _pf.resolve_weights(checkpoint, num_layers=self.pad)
+        assert self.weights.num_layers == self.pad
+        Dp = _ffi.dpitch(D)
+        self.Dp = Dp
+        e = lambda *shape, dtype=f32: torch.empty(shape, dtype=dtype, device=dev)
+        self.img = [e(H, W), e(H, W)]
+        self.feat = [e(H, W, 64), e(H, W, 64)]
+        nb = int(_ffi.lib().mccnn_features_scratch_bytes(H, W, self.pad, self.pad))
+        self.feat_scratch = e((nb + 3) // 4)
+        # volumes: A = cost volume / CBCA2 output, B = CBCA1 output / SGM in place, S = CBCA ping-pong scratch
+        self.volA = [e(H, W, Dp), e(H, W, Dp)]
+        need_b = any(s in self.stages for s in ("cbca1", "sgm", "cbca2"))
+        self.volB = [e(H, W, Dp), e(H, W, Dp)] if need_b else [None, None]
+        self.volS = e(H, W, Dp) if need_b else None
+        self.arms = [e(H, W, 4, dtype=torch.uint8), e(H, W, 4, dtype=torch.uint8)]
+        self.count = [e(H, W, dtype=torch.int32), e(H, W, dtype=torch.int32)]
+        ns = int(_ffi.lib().mccnn_sgm_scratch_bytes(H, W, D))
+        self.sgm_flags = e((ns + 3) // 4, dtype=torch.int32)
+        self.disp = [e(H, W), e(H, W)]
+        self.tmp = [e(H, W), e(H, W)]
+        self.labels = e(H, W, dtype=torch.int32)
+        self.table = _pf._to_dev(_pf.bilateral_table(5, 5, 0, self.hp["blur_sigma"]))
+        self.host_in = [torch.empty((H, W), dtype=f32, pin_memory=True) for _ in range(2)]
+        self.host_out = torch.empty((H, W), dtype=f32, pin_memory=True)
+        self.h2d_bytes = 2 * H * W * 4
+        self.d2h_bytes = H * W * 4
+        self.final_volume = None        # HWD left volume the last run's WTA / sub-pixel read
+        self.result = None
+        self._steps = self._build()
+
+    # ------------------------------------------------------------------------------------------
+    def _build(self):
+        """List of (stage name, thunk); each thunk makes the C-ABI calls of one stage."""
+        H, W, D = self.H, self.W, self.D
+        hp, p, call, sp = self.hp, _ffi.ptr, _ffi.call, _ffi.stream_ptr
+        st = self.stages
+        steps = []
+        f = ctypes.c_float
+
+        if "features" in st:
+            def features():
+                for i in range(2):
+                    call("mccnn_features", p(self.img[i]), H, W, self.pad, self.pad, self.weights.w_table,
+                         self.weights.b_table, p(self.feat[i]), p(self.feat_scratch), sp())
+            steps.append(("features", features))
+        if "cost_volume" in st:
+            def cost_volume():
+                call("mccnn_cost_volume", p(self.feat[0]), p(self.feat[1]), p(self.volA[0]), p(self.volA[1]), H, W, 64,
+                     D, sp())
+            steps.append(("cost_volume", cost_volume))
+        cur = self.volA
+        if "cbca1" in st or "cbca2" in st:
+            def arms():
+                for i in range(2):
+                    call("mccnn_cross_arms", p(self.img[i]), p(self.arms[i]), p(self.count[i]), H, W,
+                         f(np.float32(hp["cbca_intensity"])), int(hp["cbca_distance"]), sp())
+            steps.append(("cross_arms", arms))
+
+        def make_cbca(src, dst, iters):
+            def cbca():
+                for i in range(2):
+                    call("mccnn_cbca", p(src[i]), p(dst[i]), p(self.volS), p(self.arms[i]), p(self.count[i]), D, H, W,
+                         iters, sp())
+            return cbca
+
+        if "cbca1" in st:
+            steps.append(("cbca1", make_cbca(self.volA, self.volB, int(hp["cbca_num_iterations1"]))))
+            cur = self.volB
+        if "sgm" in st:
+            vol = cur
+
+            def sgm():
+                call("mccnn_sgm_average_pair", p(vol[0]), p(vol[1]), p(self.img[0]), p(self.img[1]), p(self.sgm_flags),
+                     D, H, W, float(hp["sgm_P1"]), float(hp["sgm_P2"]), float(hp["sgm_Q1"]), float(hp["sgm_Q2"]),
+                     float(hp["sgm_D"]), float(hp["sgm_V"]), sp())
+            steps.append(("sgm", sgm))
+        if "cbca2" in st:
+            dst = self.volA if cur is self.volB else self.volB
+            steps.append(("cbca2", make_cbca(cur, dst, int(hp["cbca_num_iterations2"]))))
+            cur = dst
+        self.final_volume = cur
+        d = None
+        if "wta" in st:
+            vol = cur
+
+            def wta():
+                for i in range(2):
+                    call("mccnn_wta", p(vol[i]), p(self.disp[i]), D, H, W, sp())
+            steps.append(("wta", wta))
+            d = self.disp[0]
+        if "interpolation" in st:
+            src, dst = d, self.tmp[0]
+
+            def interp():
+                call("mccnn_lr_interp", p(src), p(self.disp[1]), p(dst), p(self.labels), H, W, D, sp())
+            steps.append(("interpolation", interp))
+            d = dst
+        if "subpixel" in st:
+            src, dst, vol = d, self.tmp[1], cur
+
+            def subpixel():
+                call("mccnn_subpixel", p(src), p(vol[0]), p(dst), D, H, W, sp())
+            steps.append(("subpixel", subpixel))
+            d = dst
+        if "median" in st:
+            src = d
+            dst = self.tmp[0] if d is not self.tmp[0] else self.tmp[1]
+
+            def median():
+                call("mccnn_median", p(src), p(dst), H, W, 5, 5, sp())
+            steps.append(("median", median))
+            d = dst
+        if "bilateral" in st:
+            src = d
+            dst = self.tmp[0] if d is not self.tmp[0] else self.tmp[1]
+
+            def bilateral():
+                call("mccnn_bilateral", p(self.img[0]), p(src), p(dst), p(self.table), H, W, 5, 5,
+                     f(np.float32(hp["blur_threshold"])), sp())
+            steps.append(("bilateral", bilateral))
+            d = dst
+        self.result = d
+        return steps
+
+    # ------------------------------------------------------------------------------------------
+    def set_images(self, left_image, right_image):
+        """Copy two normalised images ([H,W,1] or [H,W]; NumPy or tensor) into the resident buffers."""
+        for i, im in enumerate((left_image, right_image)):
+            self.img[i].copy_(_pf._image2d(im))
+
+    def set_features(self, fl, fr):
+        self.feat[0].copy_(_pf._to_dev(fl))
+        self.feat[1].copy_(_pf._to_dev(fr))
+
+    def run(self):
+        """Issue the configured stages on the current stream over the resident inputs; returns the
+        device tensor holding the final disparity map (or None if no map-producing stage is enabled)."""
+        for _, fn in self._steps:
+            fn()
+        return self.result
+
+    def run_timed(self):
+        """Like run(), with a CUDA-event pair around every stage: returns {stage: milliseconds}."""
+        torch = self.torch
+        evs = []
+        for name, fn in self._steps:
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            fn()
+            b.record()
+            evs.append((name, a, b))
+        torch.cuda.synchronize()
+        return {name: a.elapsed_time(b) for name, a, b in evs}
+
+    def run_host(self, left_image, right_image):
+        """NumPy images in, NumPy disparity out: H2D from pinned memory, hot path, D2H, one sync."""
+        torch = self.torch
+        for i, im in enumerate((left_image, right_image)):
+            a = np.asarray(im, dtype=np.float32)
+            if a.ndim == 3:
+                a = a[:, :, 0]
+            self.host_in[i].numpy()[...] = a
+            self.img[i].copy_(self.host_in[i], non_blocking=True)
+        d = self.run()
+        self.host_out.copy_(d, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return self.host_out.numpy().copy()
+
+    def volume(self, which=0):
+        """Logical [D,H,W] view of the final left (0) / right (1) cost volume of the last run."""
+        return _pf._hwd_view(self.final_volume[which], self.D)
+
+
+def match_pair(left_image, right_image, ndisp, checkpoint=None, **hp):
+    """match.py:131-175 for one pair: normalised images [H,W,1] -> final left disparity map [H,W]."""
+    a = left_image
+    H, W = int(a.shape[0]), int(a.shape[1])
+    m = StereoMatcher(H, W, ndisp, checkpoint=checkpoint, **hp)
+    if _pf._is_tensor(left_image):
+        m.set_images(left_image, right_image)
+        return m.run().clone()
+    return m.run_host(left_image, right_image)
