@@ -78,9 +78,16 @@ int mccnn_cross_region_list(const uint8_t *arms, int32_t *region, int H, int W,
 
 /* ---- a5  pf:117 cost_volume_aggregation, one volume ----
  * `iters` rounds of region mean; in is left untouched, out receives the result, scratch is one
- * more HWD volume.  Flat float32 running sum in the reference's enumeration order (pf:149-163). */
+ * more HWD volume.
+ * mode MCCNN_CBCA_SEPARABLE: row sums re-used down each column (<= 54 additions per cell); equals the
+ *      reference up to float32 re-association of the sum (~1e-7 relative).  Needs the
+ *      distance_threshold the arms were built with to be <= 14 (match.py:34 default).
+ * mode MCCNN_CBCA_EXACT: one float32 running sum over the whole region in the reference's enumeration
+ *      order (pf:149-163), bit-identical to the reference (<= 729 additions per cell). */
+enum mccnn_cbca_mode { MCCNN_CBCA_SEPARABLE = 0, MCCNN_CBCA_EXACT = 1 };
 int mccnn_cbca(const float *in, float *out, float *scratch, const uint8_t *arms,
-               const int32_t *count, int D, int H, int W, int iters, void *stream);
+               const int32_t *count, int D, int H, int W, int iters, int distance_threshold, int mode,
+               void *stream);
 
 /* ---- a6  pf:476 semi_global_matching, one in-place pass over one volume ----
  * (rh, rw) in {(0,1),(0,-1),(-1,0),(1,0)}.  P1/P2/Q1/Q2/tauD arrive as doubles and are rounded to

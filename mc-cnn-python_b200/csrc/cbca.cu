@@ -8,6 +8,7 @@
 // pixels, so every lane follows the same arms (no divergence) and every load is a contiguous
 // 16 B granule of the neighbour pixel's disparity row (fully coalesced for any region shape).
 #include "common.cuh"
+#include "cbca_sep.cuh"
 
 namespace mccnn {
 
@@ -134,7 +135,11 @@ int mccnn_cross_region_list(const uint8_t *arms, int32_t *region, int H, int W, 
 }
 
 int mccnn_cbca(const float *in, float *out, float *scratch, const uint8_t *arms, const int32_t *count, int D, int H,
-               int W, int iters, void *stream) {
+               int W, int iters, int dist, int mode, void *stream) {
+    MCCNN_REQUIRE(mode == MCCNN_CBCA_SEPARABLE || mode == MCCNN_CBCA_EXACT, "cbca: unknown mode %d", mode);
+    MCCNN_REQUIRE(dist >= 1 && dist <= 255, "cbca: distance_threshold %d outside [1, 255]", dist);
+    MCCNN_REQUIRE(mode == MCCNN_CBCA_EXACT || dist <= 14,
+                  "cbca: separable mode supports distance_threshold <= 14 (got %d); use MCCNN_CBCA_EXACT", dist);
     MCCNN_REQUIRE(in && out && arms && count && D >= 1 && H >= 1 && W >= 1 && iters >= 0, "cbca: bad arguments");
     MCCNN_REQUIRE(in != out, "cbca: in and out must differ (the reference leaves its input untouched, pf:119)");
     MCCNN_REQUIRE(iters < 2 || (scratch && scratch != in && scratch != out), "cbca: scratch volume required for iters >= 2");
@@ -152,10 +157,18 @@ int mccnn_cbca(const float *in, float *out, float *scratch, const uint8_t *arms,
     const float *src = in;
     for (int it = 0; it < iters; it++) {
         float *dst = buf[it & 1];
-        k_cbca_round<<<grid, CBCA_THREADS, 0, s>>>(reinterpret_cast<const float4 *>(src),
-                                                    reinterpret_cast<float4 *>(dst),
-                                                    reinterpret_cast<const uchar4 *>(arms), count, G, H, W);
-        MCCNN_LAUNCHED("cbca_round");
+        if (mode == MCCNN_CBCA_EXACT) {
+            k_cbca_round<<<grid, CBCA_THREADS, 0, s>>>(reinterpret_cast<const float4 *>(src),
+                                                        reinterpret_cast<float4 *>(dst),
+                                                        reinterpret_cast<const uchar4 *>(arms), count, G, H, W);
+            MCCNN_LAUNCHED("cbca_round");
+        } else {
+            dim3 sgrid(cdiv(W, SEP_TW), cdiv(H, SEP_TH), cdiv(G, SEP_GC));
+            k_cbca_round_sep<<<sgrid, SEP_THREADS, 0, s>>>(reinterpret_cast<const float4 *>(src),
+                                                            reinterpret_cast<float4 *>(dst),
+                                                            reinterpret_cast<const uchar4 *>(arms), count, G, H, W);
+            MCCNN_LAUNCHED("cbca_round_sep");
+        }
         src = dst;
     }
     return MCCNN_OK;

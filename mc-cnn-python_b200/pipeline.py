@@ -30,7 +30,7 @@ STAGES = ("features", "cost_volume", "cbca1", "sgm", "cbca2", "wta", "interpolat
 
 class StereoMatcher(object):
 
-    def __init__(self, H, W, ndisp, checkpoint=None, stages=STAGES, **hp):
+    def __init__(self, H, W, ndisp, checkpoint=None, stages=STAGES, cbca_mode=None, **hp):
         torch = _pf._torch()
         self.torch = torch
         self.H, self.W, self.D = int(H), int(W), int(ndisp)
@@ -71,56 +71,97 @@ class StereoMatcher(object):
         self.host_out = torch.empty((H, W), dtype=f32, pin_memory=True)
         self.h2d_bytes = 2 * H * W * 4
         self.d2h_bytes = H * W * 4
+        self.cbca_mode = _pf.CBCA_MODE if cbca_mode is None else int(cbca_mode)
         self.final_volume = None        # HWD left volume the last run's WTA / sub-pixel read
         self.result = None
         self._steps = self._build()
 
     # ------------------------------------------------------------------------------------------
     def _build(self):
-        """List of (stage name, thunk); each thunk makes the C-ABI calls of one stage."""
+        """List of (stage name, thunk); each thunk makes the C-ABI calls of one stage.  Buffers are
+        bound when the thunk is created (factory functions, no late-binding closures)."""
         H, W, D = self.H, self.W, self.D
         hp, p, call, sp = self.hp, _ffi.ptr, _ffi.call, _ffi.stream_ptr
         st = self.stages
         steps = []
         f = ctypes.c_float
+        img, feat = self.img, self.feat
 
-        if "features" in st:
+        def make_features():
             def features():
                 for i in range(2):
-                    call("mccnn_features", p(self.img[i]), H, W, self.pad, self.pad, self.weights.w_table,
-                         self.weights.b_table, p(self.feat[i]), p(self.feat_scratch), sp())
-            steps.append(("features", features))
-        if "cost_volume" in st:
+                    call("mccnn_features", p(img[i]), H, W, self.pad, self.pad, self.weights.w_table,
+                         self.weights.b_table, p(feat[i]), p(self.feat_scratch), sp())
+            return features
+
+        def make_cost_volume(vol):
             def cost_volume():
-                call("mccnn_cost_volume", p(self.feat[0]), p(self.feat[1]), p(self.volA[0]), p(self.volA[1]), H, W, 64,
-                     D, sp())
-            steps.append(("cost_volume", cost_volume))
-        cur = self.volA
-        if "cbca1" in st or "cbca2" in st:
+                call("mccnn_cost_volume", p(feat[0]), p(feat[1]), p(vol[0]), p(vol[1]), H, W, 64, D, sp())
+            return cost_volume
+
+        def make_arms():
             def arms():
                 for i in range(2):
-                    call("mccnn_cross_arms", p(self.img[i]), p(self.arms[i]), p(self.count[i]), H, W,
+                    call("mccnn_cross_arms", p(img[i]), p(self.arms[i]), p(self.count[i]), H, W,
                          f(np.float32(hp["cbca_intensity"])), int(hp["cbca_distance"]), sp())
-            steps.append(("cross_arms", arms))
+            return arms
 
         def make_cbca(src, dst, iters):
             def cbca():
                 for i in range(2):
                     call("mccnn_cbca", p(src[i]), p(dst[i]), p(self.volS), p(self.arms[i]), p(self.count[i]), D, H, W,
-                         iters, sp())
+                         iters, int(hp["cbca_distance"]), int(self.cbca_mode), sp())
             return cbca
 
+        def make_sgm(vol):
+            def sgm():
+                call("mccnn_sgm_average_pair", p(vol[0]), p(vol[1]), p(img[0]), p(img[1]), p(self.sgm_flags),
+                     D, H, W, float(hp["sgm_P1"]), float(hp["sgm_P2"]), float(hp["sgm_Q1"]), float(hp["sgm_Q2"]),
+                     float(hp["sgm_D"]), float(hp["sgm_V"]), sp())
+            return sgm
+
+        def make_wta(vol, disp):
+            def wta():
+                for i in range(2):
+                    call("mccnn_wta", p(vol[i]), p(disp[i]), D, H, W, sp())
+            return wta
+
+        def make_interp(src, right, dst):
+            def interp():
+                call("mccnn_lr_interp", p(src), p(right), p(dst), p(self.labels), H, W, D, sp())
+            return interp
+
+        def make_subpixel(src, vol, dst):
+            def subpixel():
+                call("mccnn_subpixel", p(src), p(vol), p(dst), D, H, W, sp())
+            return subpixel
+
+        def make_median(src, dst):
+            def median():
+                call("mccnn_median", p(src), p(dst), H, W, 5, 5, sp())
+            return median
+
+        def make_bilateral(src, dst):
+            def bilateral():
+                call("mccnn_bilateral", p(img[0]), p(src), p(dst), p(self.table), H, W, 5, 5,
+                     f(np.float32(hp["blur_threshold"])), sp())
+            return bilateral
+
+        def other(d):
+            return self.tmp[0] if d is not self.tmp[0] else self.tmp[1]
+
+        if "features" in st:
+            steps.append(("features", make_features()))
+        cur = self.volA
+        if "cost_volume" in st:
+            steps.append(("cost_volume", make_cost_volume(cur)))
+        if "cbca1" in st or "cbca2" in st:
+            steps.append(("cross_arms", make_arms()))
         if "cbca1" in st:
             steps.append(("cbca1", make_cbca(self.volA, self.volB, int(hp["cbca_num_iterations1"]))))
             cur = self.volB
         if "sgm" in st:
-            vol = cur
-
-            def sgm():
-                call("mccnn_sgm_average_pair", p(vol[0]), p(vol[1]), p(self.img[0]), p(self.img[1]), p(self.sgm_flags),
-                     D, H, W, float(hp["sgm_P1"]), float(hp["sgm_P2"]), float(hp["sgm_Q1"]), float(hp["sgm_Q2"]),
-                     float(hp["sgm_D"]), float(hp["sgm_V"]), sp())
-            steps.append(("sgm", sgm))
+            steps.append(("sgm", make_sgm(cur)))
         if "cbca2" in st:
             dst = self.volA if cur is self.volB else self.volB
             steps.append(("cbca2", make_cbca(cur, dst, int(hp["cbca_num_iterations2"]))))
@@ -128,43 +169,22 @@ class StereoMatcher(object):
         self.final_volume = cur
         d = None
         if "wta" in st:
-            vol = cur
-
-            def wta():
-                for i in range(2):
-                    call("mccnn_wta", p(vol[i]), p(self.disp[i]), D, H, W, sp())
-            steps.append(("wta", wta))
+            steps.append(("wta", make_wta(cur, self.disp)))
             d = self.disp[0]
         if "interpolation" in st:
-            src, dst = d, self.tmp[0]
-
-            def interp():
-                call("mccnn_lr_interp", p(src), p(self.disp[1]), p(dst), p(self.labels), H, W, D, sp())
-            steps.append(("interpolation", interp))
-            d = dst
+            steps.append(("interpolation", make_interp(d, self.disp[1], self.tmp[0])))
+            d = self.tmp[0]
         if "subpixel" in st:
-            src, dst, vol = d, self.tmp[1], cur
-
-            def subpixel():
-                call("mccnn_subpixel", p(src), p(vol[0]), p(dst), D, H, W, sp())
-            steps.append(("subpixel", subpixel))
+            dst = other(d)
+            steps.append(("subpixel", make_subpixel(d, cur[0], dst)))
             d = dst
         if "median" in st:
-            src = d
-            dst = self.tmp[0] if d is not self.tmp[0] else self.tmp[1]
-
-            def median():
-                call("mccnn_median", p(src), p(dst), H, W, 5, 5, sp())
-            steps.append(("median", median))
+            dst = other(d)
+            steps.append(("median", make_median(d, dst)))
             d = dst
         if "bilateral" in st:
-            src = d
-            dst = self.tmp[0] if d is not self.tmp[0] else self.tmp[1]
-
-            def bilateral():
-                call("mccnn_bilateral", p(self.img[0]), p(src), p(dst), p(self.table), H, W, 5, 5,
-                     f(np.float32(hp["blur_threshold"])), sp())
-            steps.append(("bilateral", bilateral))
+            dst = other(d)
+            steps.append(("bilateral", make_bilateral(d, dst)))
             d = dst
         self.result = d
         return steps

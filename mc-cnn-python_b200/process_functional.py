@@ -26,6 +26,15 @@ __all__ = ["compute_features", "compute_cost_volume", "cost_volume_aggregation",
            "semi_global_matching", "compute_cross_region"]
 
 
+# Summation order of cross-based aggregation (mccnn_cbca `mode`):
+#   0 = "separable" (default): row sums re-used down each column, <= 54 additions per cell; differs
+#       from the reference only by float32 re-association (~1e-7 relative);
+#   1 = "exact": the reference's flat running sum over the whole region (pf:157-161), bit-identical
+#       to the reference, <= 729 additions per cell.
+CBCA_SEPARABLE, CBCA_EXACT = 0, 1
+CBCA_MODE = CBCA_SEPARABLE
+
+
 def _torch():
     import torch
     if not torch.cuda.is_available():
@@ -241,14 +250,16 @@ def compute_cross_region(image, intensity_threshold, distance_threshold):
     return _ret(region, image), _ret(count, image)
 
 
-def _cbca_one(hwd, D, arms, count, iters, out=None, scratch=None):
+def _cbca_one(hwd, D, arms, count, iters, dist, out=None, scratch=None, mode=None):
     H, W, _ = hwd.shape
     if out is None:
         out = _empty_hwd(H, W, D)
     if scratch is None and iters >= 2:
         scratch = _empty_hwd(H, W, D)
+    if mode is None:        # the separable kernel's halo is sized for match.py's distance (14); longer arms take the flat walk
+        mode = CBCA_MODE if int(dist) <= 14 else CBCA_EXACT
     _ffi.call("mccnn_cbca", _ffi.ptr(hwd), _ffi.ptr(out), _ffi.ptr(scratch), _ffi.ptr(arms), _ffi.ptr(count),
-              D, int(H), int(W), int(iters), _ffi.stream_ptr())
+              D, int(H), int(W), int(iters), int(dist), int(mode), _ffi.stream_ptr())
     return out
 
 
@@ -265,7 +276,7 @@ def cost_volume_aggregation(left_image, right_image, left_cost_volume, right_cos
         assert tuple(count.shape) == (H, W), "image and cost volume shapes differ"
         if iters >= 2 and (scratch is None or scratch.shape != hwd.shape):
             scratch = _empty_hwd(H, W, D)
-        out = _cbca_one(hwd, D, arms, count, iters, scratch=scratch)
+        out = _cbca_one(hwd, D, arms, count, iters, int(distance_threshold), scratch=scratch)
         outs.append(_ret_volume(out, D, vol))
     return outs[0], outs[1]
 

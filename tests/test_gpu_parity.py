@@ -121,7 +121,16 @@ def test_cross_regions_vs_golden(pf, oracle, pipeline_golden):
     assert eq(arms.cpu().numpy(), ao) and eq(count.cpu().numpy(), co)
 
 
-def test_cbca_bit_exact_vs_golden(pf, pipeline_golden):
+@pytest.fixture
+def exact_cbca(pf, monkeypatch):
+    """Select the flat-running-sum kernel (bit-identical to the reference) for this test."""
+    monkeypatch.setattr(pf, "CBCA_MODE", pf.CBCA_EXACT)
+
+
+CBCA_SEP_RTOL = 2e-6      # separable mode: only the association of the float32 sum differs (scale-relative)
+
+
+def test_cbca_bit_exact_vs_golden(pf, pipeline_golden, exact_cbca):
     g = pipeline_golden
     L, R = pf.cost_volume_aggregation(g["left_image"], g["right_image"], g["cv_L"], g["cv_R"], 0.02, 14, 2)
     assert eq(L, g["cbca1_L"]) and eq(R, g["cbca1_R"])
@@ -131,7 +140,7 @@ def test_cbca_bit_exact_vs_golden(pf, pipeline_golden):
 
 @pytest.mark.parametrize("H,W,D,levels,iters", [(40, 90, 70, 4, 3), (33, 47, 192, 30, 1), (21, 35, 5, 2, 4),
                                                 (6, 7, 2, 1, 2)])
-def test_cbca_bit_exact_vs_oracle(pf, oracle, H, W, D, levels, iters):
+def test_cbca_bit_exact_vs_oracle(pf, oracle, H, W, D, levels, iters, exact_cbca):
     li, ri = synth_images(H + W, H, W, levels, 2)
     rng = np.random.default_rng(D)
     L = rng.standard_normal((D, H, W)).astype(np.float32)
@@ -144,6 +153,40 @@ def test_cbca_bit_exact_vs_oracle(pf, oracle, H, W, D, levels, iters):
     # zero rounds is the identity
     L0, _ = pf.cost_volume_aggregation(li, ri, L, R, 0.02, 14, 0)
     assert eq(L0, L)
+
+
+def test_cbca_separable_vs_golden_and_oracle(pf, oracle, pipeline_golden):
+    """Default (separable) mode: same region, same order within rows and along the spine, row sums
+    formed first -> equal to the reference up to float32 re-association."""
+    assert pf.CBCA_MODE == pf.CBCA_SEPARABLE
+    g = pipeline_golden
+
+    def close(a, b):
+        scale = float(np.abs(b).max())
+        np.testing.assert_allclose(a, b, atol=CBCA_SEP_RTOL * scale, rtol=0)
+
+    L, R = pf.cost_volume_aggregation(g["left_image"], g["right_image"], g["cv_L"], g["cv_R"], 0.02, 14, 2)
+    close(L, g["cbca1_L"]); close(R, g["cbca1_R"])
+    L, R = pf.cost_volume_aggregation(g["left_image"], g["right_image"], g["sgm_L"], g["sgm_R"], 0.02, 14, 16)
+    close(L, g["cbca2_L"]); close(R, g["cbca2_R"])
+    for (H, W, D, levels, iters) in [(40, 90, 70, 4, 3), (33, 47, 192, 30, 1), (37, 29, 5, 1, 2), (50, 21, 33, 2, 5)]:
+        li, ri = synth_images(H * W, H, W, levels, 2)
+        rng = np.random.default_rng(D)
+        Lv = rng.standard_normal((D, H, W)).astype(np.float32)
+        Rv = rng.standard_normal((D, H, W)).astype(np.float32)
+        Lg, Rg = pf.cost_volume_aggregation(li, ri, Lv, Rv, 0.02, 14, iters)
+        Lo, Ro = oracle.cost_volume_aggregation(li, ri, Lv, Rv, 0.02, 14, iters)
+        close(Lg, Lo); close(Rg, Ro)
+    # integer-valued costs: sums are exact in any order -> bit-identical even in separable mode
+    Li = rng.integers(0, 64, (12, 30, 44)).astype(np.float32)
+    li, ri = synth_images(5, 30, 44, 3, 1)
+    Lg, _ = pf.cost_volume_aggregation(li, ri, Li, Li, 0.02, 14, 1)
+    Lo, _ = oracle.cost_volume_aggregation(li, ri, Li, Li, 0.02, 14, 1)
+    assert eq(Lg, Lo)
+    # arms longer than the separable kernel's halo fall back to the flat walk, still correct
+    Lg, _ = pf.cost_volume_aggregation(li, ri, Li, Li, 0.02, 20, 1)
+    Lo, _ = oracle.cost_volume_aggregation(li, ri, Li, Li, 0.02, 20, 1)
+    assert eq(Lg, Lo)
 
 
 def test_cbca_plane_constant_is_fixed_point(pf):
