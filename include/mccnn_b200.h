@@ -81,13 +81,15 @@ int mccnn_cross_region_list(const uint8_t *arms, int32_t *region, int H, int W,
  * more HWD volume.
  * mode MCCNN_CBCA_SEPARABLE: row sums re-used down each column (<= 54 additions per cell); equals the
  *      reference up to float32 re-association of the sum (~1e-7 relative).  Needs the
- *      distance_threshold the arms were built with to be <= 14 (match.py:34 default).
+ *      distance_threshold the arms were built with to be <= 14 (match.py:34 default) and a
+ *      workspace of mccnn_cbca_workspace_bytes(H, W) bytes (per-tile halo table, rebuilt per call).
  * mode MCCNN_CBCA_EXACT: one float32 running sum over the whole region in the reference's enumeration
  *      order (pf:149-163), bit-identical to the reference (<= 729 additions per cell). */
 enum mccnn_cbca_mode { MCCNN_CBCA_SEPARABLE = 0, MCCNN_CBCA_EXACT = 1 };
+size_t mccnn_cbca_workspace_bytes(int H, int W);
 int mccnn_cbca(const float *in, float *out, float *scratch, const uint8_t *arms,
                const int32_t *count, int D, int H, int W, int iters, int distance_threshold, int mode,
-               void *stream);
+               void *workspace, void *stream);
 
 /* ---- a6  pf:476 semi_global_matching, one in-place pass over one volume ----
  * (rh, rw) in {(0,1),(0,-1),(-1,0),(1,0)}.  P1/P2/Q1/Q2/tauD arrive as doubles and are rounded to

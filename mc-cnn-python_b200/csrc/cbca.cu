@@ -8,7 +8,7 @@
 // pixels, so every lane follows the same arms (no divergence) and every load is a contiguous
 // 16 B granule of the neighbour pixel's disparity row (fully coalesced for any region shape).
 #include "common.cuh"
-#include "cbca_sep.cuh"
+#include "cbca_tile.cuh"
 
 namespace mccnn {
 
@@ -134,15 +134,23 @@ int mccnn_cross_region_list(const uint8_t *arms, int32_t *region, int H, int W, 
     return MCCNN_OK;
 }
 
+size_t mccnn_cbca_workspace_bytes(int H, int W) {
+    if (H < 1 || W < 1) return 0;
+    return (size_t)cdiv(W, CT_TW) * cdiv(H, CT_TH) * sizeof(CbcaTileMeta);
+}
+
 int mccnn_cbca(const float *in, float *out, float *scratch, const uint8_t *arms, const int32_t *count, int D, int H,
-               int W, int iters, int dist, int mode, void *stream) {
+               int W, int iters, int dist, int mode, void *workspace, void *stream) {
     MCCNN_REQUIRE(mode == MCCNN_CBCA_SEPARABLE || mode == MCCNN_CBCA_EXACT, "cbca: unknown mode %d", mode);
     MCCNN_REQUIRE(dist >= 1 && dist <= 255, "cbca: distance_threshold %d outside [1, 255]", dist);
-    MCCNN_REQUIRE(mode == MCCNN_CBCA_EXACT || dist <= 14,
+    MCCNN_REQUIRE(mode == MCCNN_CBCA_EXACT || dist <= CT_MAXARM + 1,
                   "cbca: separable mode supports distance_threshold <= 14 (got %d); use MCCNN_CBCA_EXACT", dist);
     MCCNN_REQUIRE(in && out && arms && count && D >= 1 && H >= 1 && W >= 1 && iters >= 0, "cbca: bad arguments");
+    MCCNN_REQUIRE(H <= 65535 * CT_TH && W <= 65535 * CT_TW, "cbca: image too large");
     MCCNN_REQUIRE(in != out, "cbca: in and out must differ (the reference leaves its input untouched, pf:119)");
     MCCNN_REQUIRE(iters < 2 || (scratch && scratch != in && scratch != out), "cbca: scratch volume required for iters >= 2");
+    MCCNN_REQUIRE(mode == MCCNN_CBCA_EXACT || iters == 0 || workspace,
+                  "cbca: separable mode needs a workspace of mccnn_cbca_workspace_bytes(H, W) bytes");
     cudaStream_t s = (cudaStream_t)stream;
     const int Dp = dpitch(D), G = Dp / 4;
     if (iters == 0) {
@@ -150,6 +158,29 @@ int mccnn_cbca(const float *in, float *out, float *scratch, const uint8_t *arms,
         return MCCNN_OK;
     }
     dim3 grid(cdiv(W, CBCA_TW), cdiv(H, CBCA_TH));
+    int gp_top = 1;
+    while (gp_top < G && gp_top < CT_GPMAX) gp_top <<= 1;
+    const int tilesX = cdiv(W, CT_TW), tilesY = cdiv(H, CT_TH), nslab = cdiv(G, gp_top);
+    const long long nitems_ll = (long long)tilesX * tilesY * nslab;
+    MCCNN_REQUIRE(nitems_ll < (1ll << 31), "cbca: volume too large");
+    const int nitems = (int)nitems_ll;
+    static int num_sms = 0;
+    if (num_sms == 0) {
+        int dev = 0;
+        MCCNN_CUDA(cudaGetDevice(&dev));
+        MCCNN_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+    }
+    const int tgrid = nitems < num_sms * CT_CTAS_PER_SM ? nitems : num_sms * CT_CTAS_PER_SM;
+    CbcaTileMeta *meta = reinterpret_cast<CbcaTileMeta *>(workspace);
+    if (mode == MCCNN_CBCA_SEPARABLE) {
+        static bool smem_set = false;
+        if (!smem_set) {
+            MCCNN_CUDA(cudaFuncSetAttribute(k_cbca_round_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, CT_SMEM_BYTES));
+            smem_set = true;
+        }
+        k_cbca_tile_meta<<<dim3(tilesX, tilesY), 64, 0, s>>>(reinterpret_cast<const uchar4 *>(arms), meta, H, W);
+        MCCNN_LAUNCHED("cbca_tile_meta");
+    }
     // ping-pong so that the last round lands in `out`
     float *buf[2];
     buf[(iters - 1) & 1] = out;
@@ -163,11 +194,11 @@ int mccnn_cbca(const float *in, float *out, float *scratch, const uint8_t *arms,
                                                         reinterpret_cast<const uchar4 *>(arms), count, G, H, W);
             MCCNN_LAUNCHED("cbca_round");
         } else {
-            dim3 sgrid(cdiv(W, SEP_TW), cdiv(H, SEP_TH), cdiv(G, SEP_GC));
-            k_cbca_round_sep<<<sgrid, SEP_THREADS, 0, s>>>(reinterpret_cast<const float4 *>(src),
-                                                            reinterpret_cast<float4 *>(dst),
-                                                            reinterpret_cast<const uchar4 *>(arms), count, G, H, W);
-            MCCNN_LAUNCHED("cbca_round_sep");
+            k_cbca_round_tile<<<tgrid, CT_THREADS, CT_SMEM_BYTES, s>>>(reinterpret_cast<const float4 *>(src),
+                                                                        reinterpret_cast<float4 *>(dst),
+                                                                        reinterpret_cast<const uchar4 *>(arms), count, meta,
+                                                                        G, H, W, tilesX, nitems, nslab, gp_top);
+            MCCNN_LAUNCHED("cbca_round_tile");
         }
         src = dst;
     }

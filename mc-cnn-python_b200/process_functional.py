@@ -250,7 +250,14 @@ def compute_cross_region(image, intensity_threshold, distance_threshold):
     return _ret(region, image), _ret(count, image)
 
 
-def _cbca_one(hwd, D, arms, count, iters, dist, out=None, scratch=None, mode=None):
+def cbca_workspace(H, W):
+    """Per-tile halo table of the separable kernel (mccnn_cbca_workspace_bytes)."""
+    torch = _torch()
+    n = int(_ffi.lib().mccnn_cbca_workspace_bytes(int(H), int(W)))
+    return torch.empty((n + 3) // 4, dtype=torch.int32, device=_dev())
+
+
+def _cbca_one(hwd, D, arms, count, iters, dist, out=None, scratch=None, mode=None, workspace=None):
     H, W, _ = hwd.shape
     if out is None:
         out = _empty_hwd(H, W, D)
@@ -258,8 +265,10 @@ def _cbca_one(hwd, D, arms, count, iters, dist, out=None, scratch=None, mode=Non
         scratch = _empty_hwd(H, W, D)
     if mode is None:        # the separable kernel's halo is sized for match.py's distance (14); longer arms take the flat walk
         mode = CBCA_MODE if int(dist) <= 14 else CBCA_EXACT
+    if workspace is None and mode == CBCA_SEPARABLE:
+        workspace = cbca_workspace(H, W)
     _ffi.call("mccnn_cbca", _ffi.ptr(hwd), _ffi.ptr(out), _ffi.ptr(scratch), _ffi.ptr(arms), _ffi.ptr(count),
-              D, int(H), int(W), int(iters), int(dist), int(mode), _ffi.stream_ptr())
+              D, int(H), int(W), int(iters), int(dist), int(mode), _ffi.ptr(workspace), _ffi.stream_ptr())
     return out
 
 
