@@ -107,6 +107,56 @@ __global__ void __launch_bounds__(CBCA_THREADS) k_cbca_round(const float4 *__res
 
 }  // namespace mccnn
 
+
+namespace mccnn {
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess ||
+            qres != cudaDriverEntryPointSuccess)
+            return nullptr;
+        fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+
+// Tensor maps of one HWD volume for the staged-row boxes of k_cbca_round_tile:
+// [level: 4, 2, 1 granules per slab][halo class] -> box {4*stride floats, 8 + 2*halo pixels, 1 row}.
+static int build_cbca_maps(CtMaps &maps, const float *vol, int G, int H, int W) {
+    EncodeTiledFn enc = encode_tiled_fn();
+    if (!enc) {
+        set_error("cbca: cuTensorMapEncodeTiled is not available from this driver");
+        return MCCNN_ERR_CUDA;
+    }
+    const cuuint64_t Dp = (cuuint64_t)G * 4;
+    const cuuint64_t gdim[3] = {Dp, (cuuint64_t)W, (cuuint64_t)H};
+    const cuuint64_t gstr[2] = {Dp * 4, (cuuint64_t)W * Dp * 4};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    for (int l = 0; l < CT_NLEVEL; l++) {
+        const int gp = 4 >> l;
+        for (int i = 0; i < CT_NHALO; i++) {
+            const cuuint32_t box[3] = {(cuuint32_t)(4 * ct_stride(gp, G)), (cuuint32_t)(CT_TW + 2 * ct_halo(i)), 1};
+            CUresult r = enc(&maps.m[l][i], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void *)vol, gdim, gstr, box, estr,
+                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r != CUDA_SUCCESS) {
+                set_error("cbca: cuTensorMapEncodeTiled failed (%d) for box %ux%u", (int)r, box[0], box[1]);
+                return MCCNN_ERR_CUDA;
+            }
+        }
+    }
+    return MCCNN_OK;
+}
+
+}  // namespace mccnn
+
 using namespace mccnn;
 
 extern "C" {
@@ -134,9 +184,11 @@ int mccnn_cross_region_list(const uint8_t *arms, int32_t *region, int H, int W, 
     return MCCNN_OK;
 }
 
+static const int CBCA_MAX_ROUNDS = 1024;       // one tile counter per round of a call
+
 size_t mccnn_cbca_workspace_bytes(int H, int W) {
     if (H < 1 || W < 1) return 0;
-    return (size_t)cdiv(W, CT_TW) * cdiv(H, CT_TH) * sizeof(CbcaTileMeta);
+    return (size_t)cdiv(W, CT_TW) * cdiv(H, CT_TH) * sizeof(CbcaTileMeta) + CBCA_MAX_ROUNDS * sizeof(unsigned);
 }
 
 int mccnn_cbca(const float *in, float *out, float *scratch, const uint8_t *arms, const int32_t *count, int D, int H,
@@ -146,9 +198,10 @@ int mccnn_cbca(const float *in, float *out, float *scratch, const uint8_t *arms,
     MCCNN_REQUIRE(mode == MCCNN_CBCA_EXACT || dist <= CT_MAXARM + 1,
                   "cbca: separable mode supports distance_threshold <= 14 (got %d); use MCCNN_CBCA_EXACT", dist);
     MCCNN_REQUIRE(in && out && arms && count && D >= 1 && H >= 1 && W >= 1 && iters >= 0, "cbca: bad arguments");
-    MCCNN_REQUIRE(H <= 65535 * CT_TH && W <= 65535 * CT_TW, "cbca: image too large");
+    MCCNN_REQUIRE(H <= 65535 && W <= 65535, "cbca: image too large");
     MCCNN_REQUIRE(in != out, "cbca: in and out must differ (the reference leaves its input untouched, pf:119)");
     MCCNN_REQUIRE(iters < 2 || (scratch && scratch != in && scratch != out), "cbca: scratch volume required for iters >= 2");
+    MCCNN_REQUIRE(mode == MCCNN_CBCA_EXACT || iters <= CBCA_MAX_ROUNDS, "cbca: at most %d rounds per call", CBCA_MAX_ROUNDS);
     MCCNN_REQUIRE(mode == MCCNN_CBCA_EXACT || iters == 0 || workspace,
                   "cbca: separable mode needs a workspace of mccnn_cbca_workspace_bytes(H, W) bytes");
     cudaStream_t s = (cudaStream_t)stream;
@@ -157,49 +210,58 @@ int mccnn_cbca(const float *in, float *out, float *scratch, const uint8_t *arms,
         MCCNN_CUDA(cudaMemcpyAsync(out, in, (size_t)H * W * Dp * sizeof(float), cudaMemcpyDeviceToDevice, s));
         return MCCNN_OK;
     }
-    dim3 grid(cdiv(W, CBCA_TW), cdiv(H, CBCA_TH));
-    int gp_top = 1;
-    while (gp_top < G && gp_top < CT_GPMAX) gp_top <<= 1;
-    const int tilesX = cdiv(W, CT_TW), tilesY = cdiv(H, CT_TH), nslab = cdiv(G, gp_top);
-    const long long nitems_ll = (long long)tilesX * tilesY * nslab;
-    MCCNN_REQUIRE(nitems_ll < (1ll << 31), "cbca: volume too large");
-    const int nitems = (int)nitems_ll;
-    static int num_sms = 0;
-    if (num_sms == 0) {
-        int dev = 0;
-        MCCNN_CUDA(cudaGetDevice(&dev));
-        MCCNN_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
-    }
-    const int tgrid = nitems < num_sms * CT_CTAS_PER_SM ? nitems : num_sms * CT_CTAS_PER_SM;
-    CbcaTileMeta *meta = reinterpret_cast<CbcaTileMeta *>(workspace);
-    if (mode == MCCNN_CBCA_SEPARABLE) {
-        static bool smem_set = false;
-        if (!smem_set) {
-            MCCNN_CUDA(cudaFuncSetAttribute(k_cbca_round_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, CT_SMEM_BYTES));
-            smem_set = true;
-        }
-        k_cbca_tile_meta<<<dim3(tilesX, tilesY), 64, 0, s>>>(reinterpret_cast<const uchar4 *>(arms), meta, H, W);
-        MCCNN_LAUNCHED("cbca_tile_meta");
-    }
     // ping-pong so that the last round lands in `out`
     float *buf[2];
     buf[(iters - 1) & 1] = out;
     buf[iters & 1] = scratch;
     const float *src = in;
-    for (int it = 0; it < iters; it++) {
-        float *dst = buf[it & 1];
-        if (mode == MCCNN_CBCA_EXACT) {
+    if (mode == MCCNN_CBCA_EXACT) {
+        dim3 grid(cdiv(W, CBCA_TW), cdiv(H, CBCA_TH));
+        for (int it = 0; it < iters; it++) {
+            float *dst = buf[it & 1];
             k_cbca_round<<<grid, CBCA_THREADS, 0, s>>>(reinterpret_cast<const float4 *>(src),
                                                         reinterpret_cast<float4 *>(dst),
                                                         reinterpret_cast<const uchar4 *>(arms), count, G, H, W);
             MCCNN_LAUNCHED("cbca_round");
-        } else {
-            k_cbca_round_tile<<<tgrid, CT_THREADS, CT_SMEM_BYTES, s>>>(reinterpret_cast<const float4 *>(src),
-                                                                        reinterpret_cast<float4 *>(dst),
-                                                                        reinterpret_cast<const uchar4 *>(arms), count, meta,
-                                                                        G, H, W, tilesX, nitems, nslab, gp_top);
-            MCCNN_LAUNCHED("cbca_round_tile");
+            src = dst;
         }
+        return MCCNN_OK;
+    }
+
+    int gp_top = 1;
+    while (gp_top < G && gp_top < CT_GPMAX) gp_top <<= 1;
+    const int tilesX = cdiv(W, CT_TW), tilesY = cdiv(H, CT_TH), ntiles = tilesX * tilesY;
+    static int num_sms = 0;
+    static bool smem_set = false;
+    if (num_sms == 0) {
+        int dev = 0;
+        MCCNN_CUDA(cudaGetDevice(&dev));
+        MCCNN_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+    }
+    if (!smem_set) {
+        MCCNN_CUDA(cudaFuncSetAttribute(k_cbca_round_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, CT_SMEM_BYTES));
+        smem_set = true;
+    }
+    const int tgrid = ntiles < num_sms * CT_CTAS_PER_SM ? ntiles : num_sms * CT_CTAS_PER_SM;
+    CbcaTileMeta *meta = reinterpret_cast<CbcaTileMeta *>(workspace);
+    unsigned *counters = reinterpret_cast<unsigned *>(meta + ntiles);
+    MCCNN_CUDA(cudaMemsetAsync(counters, 0, (size_t)iters * sizeof(unsigned), s));
+    k_cbca_tile_meta<<<dim3(tilesX, tilesY), 64, 0, s>>>(reinterpret_cast<const uchar4 *>(arms), count, meta, G, H, W, gp_top);
+    MCCNN_LAUNCHED("cbca_tile_meta");
+    // tensor maps of the (at most three) volumes this call reads
+    const float *vols[3] = {in, iters >= 2 ? buf[0] : nullptr, iters >= 3 ? buf[1] : nullptr};
+    CtMaps maps[3];
+    for (int v = 0; v < 3; v++)
+        if (vols[v]) {
+            int rc = build_cbca_maps(maps[v], vols[v], G, H, W);
+            if (rc) return rc;
+        }
+    for (int it = 0; it < iters; it++) {
+        float *dst = buf[it & 1];
+        const int v = (src == in) ? 0 : (src == buf[0] ? 1 : 2);
+        k_cbca_round_tile<<<tgrid, CT_THREADS, CT_SMEM_BYTES, s>>>(maps[v], reinterpret_cast<float4 *>(dst), meta, G, H, W,
+                                                                    ntiles, counters + it);
+        MCCNN_LAUNCHED("cbca_round_tile");
         src = dst;
     }
     return MCCNN_OK;

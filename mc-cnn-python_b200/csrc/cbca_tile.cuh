@@ -18,69 +18,88 @@
 //       need 0-2 halo pixels, flat ones 13;
 //     - a lane schedule: the (row, pixel) items of the tile grouped into 8 bank classes (the slot
 //       of the pixel in the staged image mod 8) and, inside each class, sorted by arm length.
-//   k_cbca_round_tile: persistent CTAs (3 per SM) walk the work items (tile, slab of 4 disparity
-//       granules = 16 disparities = 64 B per pixel) in launch order with a two-stage software
-//       pipeline: while item i is being summed, all input cells of item i+1 (tile + halo, arms,
-//       counts) and the schedule of item i+2 are in flight as cp.async copies into the other
-//       shared-memory buffer, so the HBM latency of a tile is never exposed (every cell of the
-//       volume is read from HBM once; halo re-reads hit L2).
-//       One thread = one (row, pixel) item with all 4 granules in registers: the walk, its loop
-//       and index overhead are shared by 16 disparities, and the float32 adds are issued as
-//       packed FADD2.  The 8 lanes of a quarter warp take items of the 8 different bank classes
-//       (pixel stride is 5 float4, so class c, granule k lives in bank group (5c + k) mod 8 and
-//       every 16-byte access is conflict free at any walk offset), and the lanes of a warp take
-//       items of equal rank in the sorted classes, so walks inside a warp have similar length.
+//   k_cbca_round_tile: persistent CTAs walk the tiles; for each tile they walk the disparity range
+//       in slabs of 4 granules (16 disparities, 64 B per pixel) with a two-stage TMA pipeline:
+//       while slab s is being summed, the cells of slab s+1 (or of the next tile's first slab)
+//       land in the other shared-memory buffer through per-row cp.async.bulk.tensor box copies
+//       signalled on an mbarrier, so the HBM latency of a tile is never exposed and staging costs
+//       one instruction per row instead of address arithmetic per 16 bytes (every cell of the
+//       volume is read from HBM once; halo re-reads hit L2).  Out-of-image halo columns are
+//       zero-filled by the TMA unit and never summed (arms stop at the border, pf:585-620).
+//       One thread = one (row, pixel) item with all 4 granules in registers; its arm lengths and
+//       shared-memory offsets are decoded ONCE per tile and reused for every slab; the float32
+//       adds are issued as packed FADD2.  The 8 lanes of a quarter warp take items of the 8
+//       different bank classes (the box is 5 float4 wide per pixel, the 5th being padding that
+//       makes class c, granule k live in bank group (5c + k) mod 8, so every 16-byte access is
+//       conflict free at any walk offset), and the lanes of a warp take items of equal rank in
+//       the sorted classes, so walks inside a warp have similar length.
 //       Phase A writes row sums to a dense [row][8] image, phase B adds them along the spine,
 //       divides by |U| and stores 64 contiguous bytes per pixel with two 256-bit stores.
 //       A tile whose halo does not fit the shared-memory budget (flat image areas) runs the same
-//       code over 2 or 1 granules at a time instead of 4 (the extra sub-passes are not pipelined).
+//       code over 2 or 1 granules per slab instead of 4.
 //   The division by the integer |U| <= 729 is a*y refined by one FMA remainder step with
 //   y = RN(1/|U|): correctly rounded (Markstein), identical to the IEEE division the reference
 //   performs (checked against IEEE division for every |U| over 1e8 numerators); non-finite, zero
 //   and extreme magnitudes take the plain division.
 #pragma once
+#include <cuda.h>
 #include "common.cuh"
 
 namespace mccnn {
 
 constexpr int CT_TH = 16, CT_TW = 8, CT_GPMAX = 4, CT_THREADS = 128, CT_NW = CT_THREADS / 32;
+constexpr int CT_ASTEPS = (11 + CT_NW - 1) / CT_NW;   // phase A warp steps a warp may have to take
 constexpr int CT_CTAS_PER_SM = 3;
 constexpr int CT_MAXARM = 13;                                  // distance_threshold <= 14 in this mode
 constexpr int CT_MAXROWS = CT_TH + 2 * CT_MAXARM;              // 42
-constexpr int CT_IN_BYTES = 23 * 1024;                         // one staged tile + halo image
-constexpr int CT_HS_BYTES = 14 * 1024;                         // dense row sums [row][8]
+constexpr int CT_ROWS_PAD = CT_MAXROWS + 2;                    // 44
+constexpr int CT_IN_BYTES = 27 * 1024;                         // one staged slab (tile + halo), rows 128 B aligned
+constexpr int CT_HS_BYTES = 13 * 1024;                         // dense row sums [row][8]
 constexpr int CT_NONE = 0xff;
+constexpr int CT_NLEVEL = 3;                                   // gp = 4, 2, 1
+constexpr int CT_NHALO = 6;                                    // staged row halo is rounded up to one of these
+__host__ __device__ constexpr int ct_halo(int i) { return i == 0 ? 0 : i == 1 ? 1 : i == 2 ? 2 : i == 3 ? 4 : i == 4 ? 8 : 13; }
+__host__ __device__ constexpr int ct_level(int gp) { return gp == 4 ? 0 : gp == 2 ? 1 : 2; }
+// float4 per staged pixel: gp granules + one of padding (bank spreading), clamped to the volume's pitch
+__host__ __device__ constexpr int ct_stride(int gp, int G) { return gp == 1 ? 1 : (gp + 1 < G ? gp + 1 : G); }
 
-__host__ __device__ constexpr int ct_stride(int gp) { return gp == 1 ? 1 : gp + 1; }   // float4 per staged pixel
+struct CtMaps { CUtensorMap m[CT_NLEVEL][CT_NHALO]; };         // box = [4*stride floats][8 + 2*halo pixels][1 row]
 
-struct __align__(16) CbcaTileMeta {                            // 672 bytes
-    uint8_t up, down, nrows, gp;                               // halo rows, rows staged, granules per thread per sub-pass
-    uint16_t r0, total_px;                                     // first staged row, staged pixels
-    uint8_t left[CT_MAXROWS + 2], right[CT_MAXROWS + 2];       // per staged row: halo pixels
-    uint16_t centre[CT_MAXROWS + 2];                           // per staged row: slot of the tile's first column
-    uint8_t permA[8][CT_MAXROWS + 2];                          // [bank class][rank] -> staged row, longest row arms first
+struct __align__(16) CbcaTileMeta {                            // 3088 bytes, copied to shared memory as is
+    uint8_t up, down, nrows, gp;                               // halo rows, rows staged, granules per slab
+    uint16_t r0, w0, h0;                                       // first staged row, tile origin
+    uint8_t tw, th;                                            // valid tile extent
+    uint32_t stage_bytes;                                      // bytes one slab's box copies deliver
+    uint8_t hwi[CT_ROWS_PAD];                                  // per staged row: halo class (ct_halo)
+    uint16_t rowb[CT_ROWS_PAD];                                // per staged row: base, in 16-byte units
+    uint16_t centre[CT_ROWS_PAD];                              // per staged row: tile's first column, in 16-byte units
+    uint8_t permA[8][CT_ROWS_PAD];                             // [bank class][rank] -> staged row, longest row arms first
     uint8_t permB[CT_TW][CT_TH];                               // [tile column][rank] -> tile row, longest column arms first
-    uint8_t pad[8];
+    uchar4 arms[CT_MAXROWS][CT_TW];                            // arms of the staged rows at the tile's columns
+    float2 cnt[CT_TH][CT_TW];                                  // (|U|, RN(1/|U|)) of the tile's pixels
 };
-static_assert(sizeof(CbcaTileMeta) == 672, "CbcaTileMeta layout");
+static_assert(sizeof(CbcaTileMeta) == 3088, "CbcaTileMeta layout");
 
-struct __align__(16) CtStage {                                 // everything one work item needs, filled by cp.async
-    float4 in[CT_IN_BYTES / 16];
-    uchar4 arms[CT_MAXROWS][CT_TW];
-    int32_t count[CT_TH][CT_TW];
-};
-struct __align__(16) CtSmem {
-    CtStage stage[2];
+struct __align__(128) CtSmem {
+    unsigned char in[2][CT_IN_BYTES];
     float4 hs[CT_HS_BYTES / 16];
-    CbcaTileMeta meta[3];
+    CbcaTileMeta ti[2];
+    unsigned long long mbar[2];
+    int next[2];
 };
 constexpr int CT_SMEM_BYTES = (int)sizeof(CtSmem);
 
-__global__ void __launch_bounds__(64) k_cbca_tile_meta(const uchar4 *__restrict__ arms, CbcaTileMeta *__restrict__ meta,
-                                                       int H, int W) {
+// pixel of bank class q in a row whose first tile column sits at 16-byte unit c: (c + st*px) = q (mod 8)
+__device__ __forceinline__ int ct_class_px(int q, int c, int st) {
+    return (st & 1) ? ((st * (q - c)) & 7) : ((q - c) & 7);      // 1, 3, 5 are their own inverses mod 8
+}
+
+__global__ void __launch_bounds__(64) k_cbca_tile_meta(const uchar4 *__restrict__ arms, const int32_t *__restrict__ count,
+                                                       CbcaTileMeta *__restrict__ meta, int G, int H, int W, int gp_top) {
     __shared__ int s_up, s_down;
     __shared__ CbcaTileMeta m;
-    __shared__ uint8_t key[CT_MAXROWS + 2][CT_TW];
+    __shared__ uint8_t key[CT_ROWS_PAD][CT_TW];
+    __shared__ uint8_t need[CT_ROWS_PAD];
     const int tid = threadIdx.x;
     const int w0 = blockIdx.x * CT_TW, h0 = blockIdx.y * CT_TH;
     const int wend = min(w0 + CT_TW, W), hend = min(h0 + CT_TH, H), tw = wend - w0;
@@ -88,58 +107,80 @@ __global__ void __launch_bounds__(64) k_cbca_tile_meta(const uchar4 *__restrict_
     __syncthreads();
     for (int i = tid; i < CT_TH * CT_TW; i += 64) {
         const int h = h0 + i / CT_TW, w = w0 + i % CT_TW;
+        float2 c = make_float2(1.f, 1.f);
         if (h < hend && w < wend) {
             const uchar4 a = arms[(size_t)h * W + w];
             const int nu = (int)a.x - (h - h0), nd = (int)a.y - (hend - 1 - h);
             if (nu > 0) atomicMax(&s_up, nu);
             if (nd > 0) atomicMax(&s_down, nd);
+            const float n = (float)count[(size_t)h * W + w];
+            c = make_float2(n, 1.0f / n);
         }
+        m.cnt[i / CT_TW][i % CT_TW] = c;
     }
     __syncthreads();
     const int r0 = h0 - s_up;                                   // arms never leave the image (pf:585, :593)
     const int nrows = hend + s_down - r0;
     if (tid < nrows) {
         int L = 0, R = 0;
-        for (int w = w0; w < wend; w++) {
-            const uchar4 a = arms[(size_t)(r0 + tid) * W + w];
-            L = max(L, (int)a.z - (w - w0));
-            R = max(R, (int)a.w - (wend - 1 - w));
-            key[tid][w - w0] = (uint8_t)(a.z + a.w);
+        for (int px = 0; px < CT_TW; px++) {
+            uchar4 a = make_uchar4(0, 0, 0, 0);
+            if (px < tw) {
+                a = arms[(size_t)(r0 + tid) * W + w0 + px];
+                L = max(L, (int)a.z - px);
+                R = max(R, (int)a.w - (tw - 1 - px));
+            }
+            m.arms[tid][px] = a;
+            key[tid][px] = (uint8_t)(a.z + a.w);
         }
-        m.left[tid] = (uint8_t)L;
-        m.right[tid] = (uint8_t)R;
+        int hi = 0;
+        while (ct_halo(hi) < max(L, R)) hi++;
+        need[tid] = (uint8_t)hi;
     }
     __syncthreads();
     if (tid == 0) {
-        int off = 0;
-        for (int r = 0; r < nrows; r++) {
-            m.centre[r] = (uint16_t)(off + m.left[r]);
-            off += tw + m.left[r] + m.right[r];
+        int gp = gp_top, st = 1, off = 0;
+        for (;; gp >>= 1) {                                     // staged slab and dense row sums must fit
+            st = ct_stride(gp, G);
+            off = 0;
+            for (int r = 0; r < nrows; r++) off += ((CT_TW + 2 * ct_halo(need[r])) * st + 7) & ~7;
+            if (gp == 1 || (off * 16 <= CT_IN_BYTES && nrows * CT_TW * st * 16 <= CT_HS_BYTES)) break;
         }
-        m.up = (uint8_t)s_up; m.down = (uint8_t)s_down; m.nrows = (uint8_t)nrows;
-        m.r0 = (uint16_t)r0; m.total_px = (uint16_t)off;
-        int gp = CT_GPMAX;                                      // staged image and dense row sums must fit
-        while (gp > 1 && (off * ct_stride(gp) * 16 > CT_IN_BYTES || nrows * CT_TW * ct_stride(gp) * 16 > CT_HS_BYTES))
-            gp >>= 1;
-        m.gp = (uint8_t)gp;
+        off = 0;
+        unsigned bytes = 0;
+        for (int r = 0; r < nrows; r++) {
+            const int bw = CT_TW + 2 * ct_halo(need[r]);
+            m.hwi[r] = need[r];
+            m.rowb[r] = (uint16_t)off;
+            m.centre[r] = (uint16_t)(off + ct_halo(need[r]) * st);
+            off += (bw * st + 7) & ~7;
+            bytes += (unsigned)bw * st * 16;
+        }
+        m.up = (uint8_t)s_up; m.down = (uint8_t)s_down; m.nrows = (uint8_t)nrows; m.gp = (uint8_t)gp;
+        m.r0 = (uint16_t)r0; m.w0 = (uint16_t)w0; m.h0 = (uint16_t)h0;
+        m.tw = (uint8_t)tw; m.th = (uint8_t)(hend - h0);
+        m.stage_bytes = bytes;
     }
     __syncthreads();
     if (tid < 8) {
-        // phase A schedule of bank class q: one candidate per staged row, pixel (q - centre[r]) mod 8
-        const int q = tid;
+        // phase A schedule of bank class q: one candidate pixel per staged row
+        const int q = tid, st = ct_stride(m.gp, G);
         int n = 0;
+        uint8_t kk[CT_ROWS_PAD];
         for (int r = 0; r < nrows; r++) {
-            const int px = (q - m.centre[r]) & 7;
+            const int px = ct_class_px(q, m.centre[r], st);
             if (px >= tw) continue;
             const int k = key[r][px];
             int i = n++;
-            while (i > 0 && key[m.permA[q][i - 1]][(q - m.centre[m.permA[q][i - 1]]) & 7] < k) {
+            while (i > 0 && kk[i - 1] < k) {
                 m.permA[q][i] = m.permA[q][i - 1];
+                kk[i] = kk[i - 1];
                 i--;
             }
             m.permA[q][i] = (uint8_t)r;
+            kk[i] = (uint8_t)k;
         }
-        for (; n < CT_MAXROWS + 2; n++) m.permA[q][n] = CT_NONE;
+        for (; n < CT_ROWS_PAD; n++) m.permA[q][n] = CT_NONE;
     } else if (tid < 8 + CT_TW) {
         // phase B schedule of tile column px: tile rows sorted by up + down
         const int px = tid - 8;
@@ -147,7 +188,7 @@ __global__ void __launch_bounds__(64) k_cbca_tile_meta(const uchar4 *__restrict_
         uint8_t kk[CT_TH];
         if (px < tw) {
             for (int rt = 0; rt < hend - h0; rt++) {
-                const uchar4 a = arms[(size_t)(h0 + rt) * W + w0 + px];
+                const uchar4 a = m.arms[rt + s_up][px];
                 const int k = a.x + a.y;
                 int i = n++;
                 while (i > 0 && kk[i - 1] < k) {
@@ -167,15 +208,40 @@ __global__ void __launch_bounds__(64) k_cbca_tile_meta(const uchar4 *__restrict_
     for (int i = tid; i < (int)(sizeof(CbcaTileMeta) / 4); i += 64) dst[i] = src[i];
 }
 
+// ---- PTX helpers -------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned ct_smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void ct_cp_async16(void *smem_dst, const void *gmem_src) {
-    unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem_src));
-}
-__device__ __forceinline__ void ct_cp_async4(void *smem_dst, const void *gmem_src) {
-    unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(s), "l"(gmem_src));
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(ct_smem_u32(smem_dst)), "l"(gmem_src));
 }
 __device__ __forceinline__ void ct_cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
+__device__ __forceinline__ void ct_mbar_init(unsigned long long *bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(ct_smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void ct_mbar_expect_tx(unsigned long long *bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(ct_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void ct_mbar_wait(unsigned long long *bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "CT_WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, 0x989680;\n"
+        "@p bra CT_DONE_%=;\n"
+        "bra CT_WAIT_%=;\n"
+        "CT_DONE_%=:\n"
+        "}\n" ::"r"(ct_smem_u32(bar)), "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void ct_fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
+// box copy global -> shared, completion counted in bytes on the mbarrier
+__device__ __forceinline__ void ct_tma_load_3d(void *smem_dst, const CUtensorMap *map, int c0, int c1, int c2,
+                                               unsigned long long *bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];\n" ::
+            "r"(ct_smem_u32(smem_dst)), "l"(reinterpret_cast<unsigned long long>(map)), "r"(c0), "r"(c1), "r"(c2),
+        "r"(ct_smem_u32(bar))
+        : "memory");
+}
 
 struct ct_f4 { float2 lo, hi; };                                // one granule as two packed pairs
 
@@ -183,13 +249,11 @@ __device__ __forceinline__ void ct_add(ct_f4 &acc, const float4 v) {
     acc.lo = __fadd2_rn(acc.lo, make_float2(v.x, v.y));
     acc.hi = __fadd2_rn(acc.hi, make_float2(v.z, v.w));
 }
-
 __device__ __forceinline__ void ct_st256(float4 *dst, const ct_f4 a, const ct_f4 b) {
     asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(dst), "f"(a.lo.x), "f"(a.lo.y), "f"(a.hi.x),
                  "f"(a.hi.y), "f"(b.lo.x), "f"(b.lo.y), "f"(b.hi.x), "f"(b.hi.y)
                  : "memory");
 }
-
 // a / n for n = |U| (an integer <= 729), y = RN(1/n): q = RN(a*y); r = a - n*q (exact, FMA); RN(q + r*y).
 __device__ __forceinline__ float2 ct_div2(float2 a, float2 nn, float2 y) {      // nn = (-n, -n)
     const float2 q = __fmul2_rn(a, y);
@@ -197,125 +261,81 @@ __device__ __forceinline__ float2 ct_div2(float2 a, float2 nn, float2 y) {      
     return __ffma2_rn(r, y, q);
 }
 
-struct CtGeom { int G, H, W, tilesX, nslab, gp_top; };
-struct CtItem { int tile, w0, h0, tw, gslab; };
+// per-thread work of one tile, decoded once and reused for every slab
+struct CtWork {
+    unsigned a_in[CT_ASTEPS], a_hs[CT_ASTEPS];      // phase A items: 16-byte-unit offsets of the centre cell / of the row-sum cell
+    unsigned a_lr[CT_ASTEPS];               // left | right << 8 | valid << 16
+    unsigned b_hs, b_ud;            // phase B item: row-sum cell; up | down << 8 | valid << 16
+    float b_n, b_y;
+    float4 *b_out;                  // output cell of slab 0
+};
 
-__device__ __forceinline__ CtItem ct_item(int it, const CtGeom &ge) {
-    CtItem x;
-    x.tile = it / ge.nslab;
-    x.gslab = (it - x.tile * ge.nslab) * ge.gp_top;
-    const int ty = x.tile / ge.tilesX, tx = x.tile - ty * ge.tilesX;
-    x.w0 = tx * CT_TW; x.h0 = ty * CT_TH;
-    x.tw = min(x.w0 + CT_TW, ge.W) - x.w0;
-    return x;
+// warp 0: issue the box copies of one slab (granules from g0) of tile `m` into `dst`
+__device__ __forceinline__ void ct_issue_slab(const CtMaps &maps, const CbcaTileMeta &m, int g0, int G,
+                                              unsigned char *dst, unsigned long long *bar) {
+    const int lane = threadIdx.x & 31;
+    const int level = ct_level(m.gp);
+    ct_fence_proxy_async();                                     // earlier generic reads of dst are ordered by the barrier
+    for (int r = lane; r < m.nrows; r += 32) {
+        const int hi = m.hwi[r];
+        ct_tma_load_3d(dst + (size_t)m.rowb[r] * 16, &maps.m[level][hi], 4 * g0, (int)m.w0 - ct_halo(hi), (int)m.r0 + r, bar);
+    }
+    if (lane == 0) ct_mbar_expect_tx(bar, m.stage_bytes);
 }
 
-// cp.async the cells of one sub-pass (GP granules from g0, ng live) of an item: one warp per row,
-// lanes = (pixel, granule), granule fastest.  No wait here.
+// acc = sum of the n cells of a walk, in the reference's order: p0, p0 - step, .., p0 - l*step, p0 + step, .., the
+// adds strictly sequential per element (same rounding as a plain loop).
 template <int GP>
-__device__ __forceinline__ void ct_stage_cells(const float4 *__restrict__ in, float4 *in_s, const CbcaTileMeta &m,
-                                               const CtItem &x, int g0, int ng, const CtGeom &ge) {
-    constexpr int ST = ct_stride(GP), PPW = 32 / GP;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int k = lane % GP, sub = lane / GP;
-    if (k >= ng) return;
-    const int nrows = m.nrows;
-    const float4 *base = in + ((size_t)m.r0 * ge.W + x.w0 + sub) * ge.G + g0 + k;
-    for (int r = warp; r < nrows; r += CT_NW) {
-        const int L = m.left[r];
-        const int npx = x.tw + L + m.right[r];
-        const float4 *src = base + ((ptrdiff_t)r * ge.W - L) * (ptrdiff_t)ge.G;
-        float4 *dst = in_s + (m.centre[r] - L + sub) * ST + k;
-        for (int px = sub; px < npx; px += PPW) {
-            ct_cp_async16(dst, src);
-            src += (size_t)PPW * ge.G;
-            dst += PPW * ST;
+__device__ __forceinline__ void ct_walk(ct_f4 (&acc)[GP], const float4 *p0, int step, int l, int n) {
+#pragma unroll
+    for (int k = 0; k < GP; k++) acc[k].lo = acc[k].hi = make_float2(0.f, 0.f);
+#pragma unroll 1
+    for (int i = 0; i < n; i += 2) {
+        const int i1 = i + 1;
+        const bool two = i1 < n;
+        const int o0 = (i <= l) ? -i : i - l;
+        const int o1 = two ? ((i1 <= l) ? -i1 : i1 - l) : o0;
+        const float4 *pa = p0 + o0 * step, *pb = p0 + o1 * step;
+        float4 a[GP], b[GP];
+#pragma unroll
+        for (int k = 0; k < GP; k++) a[k] = pa[k];
+#pragma unroll
+        for (int k = 0; k < GP; k++) b[k] = pb[k];
+#pragma unroll
+        for (int k = 0; k < GP; k++) ct_add(acc[k], a[k]);
+        if (two) {
+#pragma unroll
+            for (int k = 0; k < GP; k++) ct_add(acc[k], b[k]);
         }
     }
 }
-__device__ __forceinline__ void ct_stage_cells_gp(int gp, const float4 *__restrict__ in, float4 *in_s,
-                                                  const CbcaTileMeta &m, const CtItem &x, int g0, int ng,
-                                                  const CtGeom &ge) {
-    if (gp == 4) ct_stage_cells<4>(in, in_s, m, x, g0, ng, ge);
-    else if (gp == 2) ct_stage_cells<2>(in, in_s, m, x, g0, ng, ge);
-    else ct_stage_cells<1>(in, in_s, m, x, g0, ng, ge);
-}
 
-// arms of the staged rows and |U| of the tile pixels (4-byte cp.async: no alignment assumption on W)
-__device__ __forceinline__ void ct_stage_aux(const uchar4 *__restrict__ arms, const int32_t *__restrict__ count,
-                                             CtStage &st, const CbcaTileMeta &m, const CtItem &x, const CtGeom &ge) {
-    const int tid = threadIdx.x;
-    const int n = m.nrows * CT_TW;
-    for (int i = tid; i < n; i += CT_THREADS) {
-        const int r = i / CT_TW, px = i % CT_TW;
-        if (px < x.tw) ct_cp_async4(&st.arms[r][px], arms + (size_t)(m.r0 + r) * ge.W + x.w0 + px);
-    }
-    {
-        const int r = tid / CT_TW, px = tid % CT_TW;
-        if (x.h0 + r < ge.H && px < x.tw) ct_cp_async4(&st.count[r][px], count + (size_t)(x.h0 + r) * ge.W + x.w0 + px);
-    }
-}
-
-// phase A + B of one sub-pass over GP granules per pixel starting at granule g0 (ng <= GP of them live);
-// the caller has made the staged cells visible (wait + barrier).
 template <int GP>
-__device__ __forceinline__ void ct_compute(float4 *__restrict__ out, const CtStage &st, float4 *hs_s, const CbcaTileMeta &m,
-                                           const CtItem &x, int g0, int ng, const CtGeom &ge) {
-    constexpr int ST = ct_stride(GP);
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int nrows = m.nrows;
-    const int q = lane & 7, rk = lane >> 3;                      // bank class / tile column, rank within the warp step
-    // ---- phase A: row sums, order w, w-1, .., w-left, w+1, .., w+right (pf:645-650)
-    for (int t = warp; t * 4 < nrows; t += CT_NW) {
-        const int r = m.permA[q][t * 4 + rk];
-        if (r == CT_NONE) continue;
-        const int c = m.centre[r];
-        const int px = (q - c) & 7;
-        const uchar4 a = st.arms[r][px];
-        const float4 *p0 = st.in + (c + px) * ST;
+__device__ __forceinline__ void ct_slab(const float4 *in_s, float4 *hs_s, const CtWork &wk, int st, int slab, int ng, int G) {
+    // ---- phase A: row sums, order w, w-1, .., w-left, w+1, .., w+right (pf:645-650).  One loop over the
+    //      left + right + 1 cells of the walk (lanes of a warp have similar totals, not similar splits),
+    //      two cells per trip with the loads issued ahead of the adds.
+#pragma unroll
+    for (int i = 0; i < CT_ASTEPS; i++) {
+        if (!(wk.a_lr[i] >> 16)) continue;
+        const float4 *p0 = in_s + wk.a_in[i];
+        const int l = wk.a_lr[i] & 0xff, n = l + ((wk.a_lr[i] >> 8) & 0xff) + 1;
         ct_f4 acc[GP];
+        ct_walk<GP>(acc, p0, st, l, n);
+        float4 *d = hs_s + wk.a_hs[i];
 #pragma unroll
-        for (int k = 0; k < GP; k++) acc[k].lo = acc[k].hi = make_float2(0.f, 0.f);
-        const float4 *p = p0;
-#pragma unroll 1
-        for (int j = a.z; j >= 0; j--, p -= ST) {
-#pragma unroll
-            for (int k = 0; k < GP; k++) ct_add(acc[k], p[k]);
-        }
-        p = p0 + ST;
-#pragma unroll 1
-        for (int j = a.w; j > 0; j--, p += ST) {
-#pragma unroll
-            for (int k = 0; k < GP; k++) ct_add(acc[k], p[k]);
-        }
-        float4 *d = hs_s + (r * CT_TW + px) * ST;
-#pragma unroll
-        for (int k = 0; k < GP; k++) d[k] = make_float4(acc[k].lo.x, acc[k].lo.y, acc[k].hi.x, acc[k].hi.y);
+        for (int k = 0; k < GP; k++)                             // (a pixel has min(GP + 1, G) cells: never write past ng)
+            if (k < ng) d[k] = make_float4(acc[k].lo.x, acc[k].lo.y, acc[k].hi.x, acc[k].hi.y);
     }
     __syncthreads();
 
     // ---- phase B: column sums in spine order h, h-1, .., h-up, h+1, .., h+down (pf:640-644), / |U|
-    const int rt = m.permB[q][warp * 4 + rk];                    // 16 ranks = 4 warps x 4
-    if (rt != CT_NONE) {
-        const int px = q, r = rt + m.up;
-        const uchar4 a = st.arms[r][px];
-        const float4 *p0 = hs_s + (r * CT_TW + px) * ST;
+    if (wk.b_ud >> 16) {
+        const float4 *p0 = hs_s + wk.b_hs;
+        const int u = wk.b_ud & 0xff, cells = u + ((wk.b_ud >> 8) & 0xff) + 1;
         ct_f4 acc[GP];
-#pragma unroll
-        for (int k = 0; k < GP; k++) acc[k].lo = acc[k].hi = make_float2(0.f, 0.f);
-        const float4 *p = p0;
-#pragma unroll 1
-        for (int j = a.x; j >= 0; j--, p -= CT_TW * ST) {
-#pragma unroll
-            for (int k = 0; k < GP; k++) ct_add(acc[k], p[k]);
-        }
-        p = p0 + CT_TW * ST;
-#pragma unroll 1
-        for (int j = a.y; j > 0; j--, p += CT_TW * ST) {
-#pragma unroll
-            for (int k = 0; k < GP; k++) ct_add(acc[k], p[k]);
-        }
-        const float n = (float)st.count[rt][px], y = 1.0f / n;
+        ct_walk<GP>(acc, p0, CT_TW * st, u, cells);
+        const float n = wk.b_n, y = wk.b_y;
         float hi = 0.f, lo = 3e38f;
 #pragma unroll
         for (int k = 0; k < GP; k++) {
@@ -333,8 +353,8 @@ __device__ __forceinline__ void ct_compute(float4 *__restrict__ out, const CtSta
                 acc[k].hi = make_float2(acc[k].hi.x / n, acc[k].hi.y / n);
             }
         }
-        float4 *dst = out + ((size_t)(x.h0 + rt) * ge.W + x.w0 + px) * ge.G + g0;
-        if (GP >= 2 && ng == GP && !(ge.G & 1)) {
+        float4 *dst = wk.b_out + slab * GP;
+        if (GP >= 2 && ng == GP && !(G & 1)) {
 #pragma unroll
             for (int k = 0; k < GP; k += 2) ct_st256(dst + k, acc[k], acc[k + 1 < GP ? k + 1 : k]);
         } else {
@@ -344,70 +364,97 @@ __device__ __forceinline__ void ct_compute(float4 *__restrict__ out, const CtSta
         }
     }
 }
-__device__ __forceinline__ void ct_compute_gp(int gp, float4 *__restrict__ out, const CtStage &st, float4 *hs_s,
-                                              const CbcaTileMeta &m, const CtItem &x, int g0, int ng, const CtGeom &ge) {
-    if (gp == 4) ct_compute<4>(out, st, hs_s, m, x, g0, ng, ge);
-    else if (gp == 2) ct_compute<2>(out, st, hs_s, m, x, g0, ng, ge);
-    else ct_compute<1>(out, st, hs_s, m, x, g0, ng, ge);
-}
 
-// Persistent: CTA b takes work items b, b + gridDim.x, ...; item = (tile, slab), the slabs of a tile
-// adjacent in the order so that the pieces of a pixel's disparity row are read and written close
-// together in time.  gp_top = granules per slab (4, or the next power of two >= G for small ndisp).
+// Persistent: CTA b starts with tile b and then takes tiles from a global counter (tiles differ a lot in
+// cost: flat image areas have long arms), two tiles ahead of the one being summed.  Neighbouring tiles run
+// at the same time on different SMs, so halo re-reads hit L2.  Each tile is walked over all its slabs.
 __global__ void __launch_bounds__(CT_THREADS, CT_CTAS_PER_SM)
-k_cbca_round_tile(const float4 *__restrict__ in, float4 *__restrict__ out, const uchar4 *__restrict__ arms,
-                  const int32_t *__restrict__ count, const CbcaTileMeta *__restrict__ meta, int G, int H, int W,
-                  int tilesX, int nitems, int nslab, int gp_top) {
-    extern __shared__ __align__(16) unsigned char ct_raw[];
+k_cbca_round_tile(const __grid_constant__ CtMaps maps, float4 *__restrict__ out, const CbcaTileMeta *__restrict__ meta,
+                  int G, int H, int W, int ntiles, unsigned *__restrict__ counter) {
+    extern __shared__ __align__(128) unsigned char ct_raw[];
     CtSmem &sm = *reinterpret_cast<CtSmem *>(ct_raw);
-    const int tid = threadIdx.x;
-    CtGeom ge;
-    ge.G = G; ge.H = H; ge.W = W; ge.tilesX = tilesX; ge.nslab = nslab; ge.gp_top = gp_top;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int first = blockIdx.x, step = gridDim.x;
-    if (first >= nitems) return;
+    if (first >= ntiles) return;
 
-    auto fetch_meta = [&](int it, int slot) {                    // 42 x 16 B
-        const float4 *src = reinterpret_cast<const float4 *>(meta + it / nslab);
-        float4 *dst = reinterpret_cast<float4 *>(&sm.meta[slot]);
-        if (tid < (int)(sizeof(CbcaTileMeta) / 16)) ct_cp_async16(dst + tid, src + tid);
-    };
-    auto stage_item = [&](int it, int n) {                       // first sub-pass of item `it` (its n-th of this CTA)
-        const CbcaTileMeta &m = sm.meta[n % 3];
-        const CtItem x = ct_item(it, ge);
-        const int gp = min((int)m.gp, gp_top);
-        ct_stage_cells_gp(gp, in, sm.stage[n & 1].in, m, x, x.gslab, min(gp, G - x.gslab), ge);
-        ct_stage_aux(arms, count, sm.stage[n & 1], m, x, ge);
+    auto fetch_ti = [&](int tile, int slot) {                    // 193 x 16 B
+        const float4 *src = reinterpret_cast<const float4 *>(meta + tile);
+        float4 *dst = reinterpret_cast<float4 *>(&sm.ti[slot]);
+        for (int i = tid; i < (int)(sizeof(CbcaTileMeta) / 16); i += CT_THREADS) ct_cp_async16(dst + i, src + i);
     };
 
-    // prologue: schedule of items 0 and 1, cells of item 0
-    fetch_meta(first, 0);
-    if (first + step < nitems) fetch_meta(first + step, 1);
+    if (tid == 0) {
+        ct_mbar_init(&sm.mbar[0], 1);
+        ct_mbar_init(&sm.mbar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    if (tid == 0) sm.next[0] = (int)atomicAdd(counter, 1u) + step;
+    fetch_ti(first, 0);
     ct_cp_async_wait_all();
     __syncthreads();
-    stage_item(first, 0);
+    unsigned c = 0;                                             // slabs issued so far: buffer c & 1, phase (c >> 1) & 1
+    if (warp == 0) ct_issue_slab(maps, sm.ti[0], 0, G, sm.in[0], &sm.mbar[0]);
 
-    int n = 0;
-    for (int it = first; it < nitems; it += step, n++) {
-        ct_cp_async_wait_all();
-        __syncthreads();                                        // item n staged, schedule n+1 present, buffers of n-1 free
-        if (it + step < nitems) stage_item(it + step, n + 1);
-        if (it + 2 * step < nitems) fetch_meta(it + 2 * step, (n + 2) % 3);
-        const CbcaTileMeta &m = sm.meta[n % 3];
-        const CtItem x = ct_item(it, ge);
-        const int gp = min((int)m.gp, gp_top);
-        CtStage &st = sm.stage[n & 1];
-        ct_compute_gp(gp, out, st, sm.hs, m, x, x.gslab, min(gp, G - x.gslab), ge);
-        // remaining sub-passes of a tile that did not fit at gp_top granules (not pipelined)
-        for (int sub = gp; sub < gp_top && x.gslab + sub < G; sub += gp) {
-            const int g0 = x.gslab + sub;
-            __syncthreads();                                    // everyone done with st.in and hs
-            ct_stage_cells_gp(gp, in, st.in, m, x, g0, min(gp, G - g0), ge);
-            ct_cp_async_wait_all();
-            __syncthreads();
-            ct_compute_gp(gp, out, st, sm.hs, m, x, g0, min(gp, G - g0), ge);
+    int tile = first;
+    for (int n = 0; tile < ntiles; n++) {
+        const CbcaTileMeta &m = sm.ti[n & 1];
+        const int next_tile = sm.next[n & 1];
+        const bool has_next = next_tile < ntiles;
+        if (has_next) fetch_ti(next_tile, (n + 1) & 1);          // lands while this tile's slabs are summed
+        int after_next = 0;
+        if (tid == 0) after_next = (int)atomicAdd(counter, 1u) + step;
+        const int gp = m.gp, st = ct_stride(gp, G);
+        const int nslab = (G + gp - 1) / gp;
+
+        // ---- decode this thread's items once per tile
+        CtWork wk;
+        const int q = lane & 7, rk = lane >> 3;
+#pragma unroll
+        for (int i = 0; i < CT_ASTEPS; i++) {
+            const int t = warp + i * CT_NW;
+            wk.a_lr[i] = 0; wk.a_in[i] = 0; wk.a_hs[i] = 0;
+            if (t * 4 < m.nrows) {
+                const int r = m.permA[q][t * 4 + rk];
+                if (r != CT_NONE) {
+                    const int cc = m.centre[r];
+                    const int px = ct_class_px(q, cc, st);
+                    const uchar4 a = m.arms[r][px];
+                    wk.a_in[i] = cc + px * st;
+                    wk.a_hs[i] = (r * CT_TW + px) * st;
+                    wk.a_lr[i] = a.z | (a.w << 8) | (1u << 16);
+                }
+            }
         }
+        {
+            const int rt = warp < 4 ? m.permB[q][warp * 4 + rk] : CT_NONE;   // 16 ranks = 4 warps x 4
+            wk.b_ud = 0; wk.b_hs = 0; wk.b_n = 1.f; wk.b_y = 1.f; wk.b_out = out;
+            if (rt != CT_NONE) {
+                const int r = rt + m.up;
+                const uchar4 a = m.arms[r][q];
+                wk.b_hs = (r * CT_TW + q) * st;
+                wk.b_ud = a.x | (a.y << 8) | (1u << 16);
+                wk.b_n = m.cnt[rt][q].x; wk.b_y = m.cnt[rt][q].y;
+                wk.b_out = out + ((size_t)(m.h0 + rt) * W + m.w0 + q) * G;
+            }
+        }
+
+        for (int s = 0; s < nslab; s++, c++) {
+            ct_mbar_wait(&sm.mbar[c & 1], (c >> 1) & 1);         // this slab's cells have landed
+            ct_cp_async_wait_all();                             // (this thread's part of the next tile's schedule)
+            if (tid == 0 && s == nslab - 1) sm.next[(n + 1) & 1] = after_next;
+            __syncthreads();                                    // previous slab fully consumed; next schedule visible
+            if (warp == 0) {
+                if (s + 1 < nslab) ct_issue_slab(maps, m, (s + 1) * gp, G, sm.in[(c + 1) & 1], &sm.mbar[(c + 1) & 1]);
+                else if (has_next) ct_issue_slab(maps, sm.ti[(n + 1) & 1], 0, G, sm.in[(c + 1) & 1], &sm.mbar[(c + 1) & 1]);
+            }
+            const float4 *in_s = reinterpret_cast<const float4 *>(sm.in[c & 1]);
+            const int ng = min(gp, G - s * gp);
+            if (gp == 4) ct_slab<4>(in_s, sm.hs, wk, st, s, ng, G);
+            else if (gp == 2) ct_slab<2>(in_s, sm.hs, wk, st, s, ng, G);
+            else ct_slab<1>(in_s, sm.hs, wk, st, s, ng, G);
+        }
+        tile = next_tile;
     }
-    ct_cp_async_wait_all();
 }
 
 }  // namespace mccnn
