@@ -2,121 +2,273 @@
 // R[d,h,w] = L[d,h,w+d]  (w < W-d), the invalid triangles filled by the 3-tap mean recurrence
 // (pf:94-95, :105-106).  Volumes are written in the HWD layout.
 //
-// k_cost_volume: one CTA per (row h, 32-pixel tile).  The 64-channel feature rows of the tile
-// (left) and of the 32+D pixels it can match (right) are staged once in shared memory with
-// 16-byte cp.async copies (XOR-swizzled so that the float4 reads below are conflict free).  Each
-// thread owns a 4(w) x 8(d) register tile: along the diagonals w-d the right-image pixel is the
-// same, so 11 right pixels feed 32 outputs.  Every product is computed once and stored twice:
-// L directly from registers (two 16 B stores per pixel), R through a shared-memory transpose so
-// that each warp writes a contiguous run of disparities of one right-image pixel.
+// The stage is 8 + 512/D bytes and 128 flop per cell: at the float32-SIMT ridge of B200, so the dot
+// products run on the tensor cores and the kernel is left with what it should be bound by -- writing
+// the two volumes.  For one image row the scores are a banded slice of the GEMM
+// S = FL[h] (W x 64) . FR[h]^T (64 x W): only x = w - d with 0 <= d < ndisp is needed.
+//
+// k_cost_volume_tc: persistent, one CTA per SM, 256 threads in two groups.
+//   front end (warps 0-3): TMA (cp.async.bulk.tensor, 128B swizzle) brings the 128-pixel left tile and,
+//       128 right pixels at a time, the right rows it can match; the float32 operands are split in
+//       shared memory into hi = tf32(x) and lo = x - hi (exact), and one thread issues tcgen05.mma
+//       kind::tf32 three times per K step -- hi.hi + hi.lo + lo.hi, accumulated in float32 in TMEM --
+//       which restores float32-level accuracy (error ~1e-6 of the volume's scale; plain TF32 would
+//       break the 1e-4 gate).  Accumulators are double buffered in TMEM so the
+//       next chunk is loaded, split and multiplied while the previous one is written out.
+//   epilogue (warps 4-7, one per TMEM lane quarter): tcgen05.ld 32 columns at a time.  A TMEM column
+//       is one right pixel x and the 32 lanes of a warp are consecutive left pixels w, i.e.
+//       consecutive d = w - x: R[h][x][d..d+31] is one coalesced 128-byte store straight from
+//       registers.  L[h][w][.] needs the transpose: values go through a padded shared-memory tile
+//       and leave as 128-byte runs of consecutive d per pixel.  Column groups whose d range lies
+//       outside [0, ndisp) are skipped.  The negation (pf:111-112) is folded into the stores.
+// k_cost_fill then overwrites the cells that have no correspondent.
+#include <cuda.h>
 #include "common.cuh"
 
 namespace mccnn {
 
-constexpr int CV_TWB = 32;      // pixels per CTA tile
-constexpr int CV_C = 64;        // feature channels (model.py:38)
+constexpr int CV_C = 64;                   // feature channels (model.py:38)
+constexpr int CV_BM = 128;                 // left pixels per tile (MMA M, TMEM lanes)
+constexpr int CV_BN = 128;                 // right pixels per chunk (MMA N, TMEM columns)
+constexpr int CV_KB_BYTES = 128 * 128;     // one K block: 128 rows x 32 floats, 128B-swizzled
+constexpr int CV_TILE_BYTES = 2 * CV_KB_BYTES;
+constexpr int CV_LS_PITCH = CV_BN + 1;     // staging tile pitch (floats): conflict-free transposed writes
+constexpr int CV_THREADS = 256;
 
-__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src) {
-    unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem_src));
+struct __align__(1024) CvSmem {
+    unsigned char a_hi[CV_TILE_BYTES], a_lo[CV_TILE_BYTES], b_hi[CV_TILE_BYTES], b_lo[CV_TILE_BYTES];
+    float ls[CV_BM * CV_LS_PITCH];
+    unsigned long long bar_tma_a, bar_tma_b, bar_full[2], bar_empty[2];
+    unsigned tmem_base;
+};
+
+struct CvMaps { CUtensorMap fl, fr; };      // [H][W][64] float32, box {32 channels, 128 pixels, 1 row}, SWIZZLE_128B
+
+__device__ __forceinline__ unsigned cv_smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void cv_mbar_init(unsigned long long *bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(cv_smem_u32(bar)), "r"(count));
 }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
+__device__ __forceinline__ void cv_mbar_expect_tx(unsigned long long *bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(cv_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void cv_mbar_arrive(unsigned long long *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(cv_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void cv_mbar_wait(unsigned long long *bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "CV_WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, 0x989680;\n"
+        "@p bra CV_DONE_%=;\n"
+        "bra CV_WAIT_%=;\n"
+        "CV_DONE_%=:\n"
+        "}\n" ::"r"(cv_smem_u32(bar)), "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void cv_tma_load_3d(void *smem_dst, const CUtensorMap *map, int c0, int c1, int c2,
+                                               unsigned long long *bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];\n" ::
+            "r"(cv_smem_u32(smem_dst)), "l"(reinterpret_cast<unsigned long long>(map)), "r"(c0), "r"(c1), "r"(c2),
+        "r"(cv_smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ void cv_named_barrier(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;\n" ::"r"(id), "r"(nthreads) : "memory");
+}
+// K-major, 128B-swizzled operand: rows of 128 bytes, 8-row groups 1024 bytes apart
+__device__ __forceinline__ unsigned long long cv_smem_desc(unsigned smem_addr) {
+    unsigned long long d = 0;
+    d |= (unsigned long long)((smem_addr >> 4) & 0x3fff);
+    d |= (unsigned long long)1 << 16;                     // leading byte offset (unused for swizzled K-major)
+    d |= (unsigned long long)(1024 >> 4) << 32;           // stride byte offset between 8-row groups
+    d |= (unsigned long long)1 << 46;                     // descriptor version (sm_100)
+    d |= (unsigned long long)2 << 61;                     // SWIZZLE_128B
+    return d;
+}
+// D[tmem] (+)= A[smem] . B[smem]^T, M = 128, N = 128, K = 8 (tf32)
+__device__ __forceinline__ void cv_mma_tf32(unsigned tmem_d, unsigned long long a_desc, unsigned long long b_desc,
+                                            unsigned idesc, unsigned accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void cv_mma_commit(unsigned long long *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(cv_smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void cv_tmem_ld32(unsigned taddr, unsigned (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+}
 
-// float4 chunk c4 (0..15) of staged pixel r lives at chunk (c4 ^ ((r >> 2) & 7)) of row r.
-__device__ __forceinline__ int swz(int r, int c4) { return r * 16 + (c4 ^ ((r >> 2) & 7)); }
-
-__global__ void __launch_bounds__(512) k_cost_volume(const float *__restrict__ fl, const float *__restrict__ fr,
-                                                     float *__restrict__ L, float *__restrict__ R, int H, int W, int D,
-                                                     int Dp, int Dr) {
-    extern __shared__ float4 smem4[];
-    float4 *As = smem4;                         // [32][16] float4
-    float4 *Bs = smem4 + CV_TWB * 16;           // [32 + Dr][16] float4 ; later reused as the output tile
-    const int h = blockIdx.y, w0 = blockIdx.x * CV_TWB;
-    const int xb0 = w0 - Dr;                    // first staged right-image pixel
-    const int NB = CV_TWB + Dr;
-    const int tid = threadIdx.x, nthr = blockDim.x;
-
-    // ---- stage the feature rows
-    const float4 *flrow = reinterpret_cast<const float4 *>(fl) + (size_t)h * W * 16;
-    const float4 *frrow = reinterpret_cast<const float4 *>(fr) + (size_t)h * W * 16;
-    for (int i = tid; i < CV_TWB * 16; i += nthr) {
-        int r = i >> 4, c4 = i & 15, w = w0 + r;
-        if (w < W) cp_async16(&As[swz(r, c4)], flrow + (size_t)w * 16 + c4);
-        else As[swz(r, c4)] = make_float4(0.f, 0.f, 0.f, 0.f);
+// hi = tf32(x) in place, lo = x - hi (exact) at the same offset of `lo` (the swizzle permutes 16-byte chunks only)
+__device__ __forceinline__ void cv_split_tile(unsigned char *hi, unsigned char *lo, int ftid) {
+    float4 *h4 = reinterpret_cast<float4 *>(hi);
+    float4 *l4 = reinterpret_cast<float4 *>(lo);
+#pragma unroll 4
+    for (int i = ftid; i < CV_TILE_BYTES / 16; i += 128) {
+        const float4 x = h4[i];
+        unsigned a, b, c, d;
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(a) : "f"(x.x));
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(b) : "f"(x.y));
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(c) : "f"(x.z));
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(d) : "f"(x.w));
+        const float4 hv = make_float4(__uint_as_float(a), __uint_as_float(b), __uint_as_float(c), __uint_as_float(d));
+        h4[i] = hv;
+        l4[i] = make_float4(x.x - hv.x, x.y - hv.y, x.z - hv.z, x.w - hv.w);
     }
-    for (int i = tid; i < NB * 16; i += nthr) {
-        int r = i >> 4, c4 = i & 15, x = xb0 + r;
-        if (x >= 0 && x < W) cp_async16(&Bs[swz(r, c4)], frrow + (size_t)x * 16 + c4);
-        else Bs[swz(r, c4)] = make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
+__global__ void __launch_bounds__(CV_THREADS, 1)
+k_cost_volume_tc(const __grid_constant__ CvMaps maps, float *__restrict__ L, float *__restrict__ R, int H, int W, int D,
+                 int Dp, int nwt, int nchunks, int ntiles) {
+    extern __shared__ __align__(1024) unsigned char cv_raw[];
+    CvSmem &sm = *reinterpret_cast<CvSmem *>(cv_raw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(cv_smem_u32(&sm.tmem_base)),
+                     "r"(2 * CV_BN)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
     }
-    cp_async_wait_all();
+    if (tid == 32) {
+        cv_mbar_init(&sm.bar_tma_a, 1);
+        cv_mbar_init(&sm.bar_tma_b, 1);
+        cv_mbar_init(&sm.bar_full[0], 1);
+        cv_mbar_init(&sm.bar_full[1], 1);
+        cv_mbar_init(&sm.bar_empty[0], 128);
+        cv_mbar_init(&sm.bar_empty[1], 128);
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
     __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+    const unsigned tmem_base = sm.tmem_base;
+    // instruction descriptor: D = F32, A = B = TF32, both K-major, N = 128, M = 128
+    const unsigned idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((unsigned)(CV_BN >> 3) << 17) | ((unsigned)(CV_BM >> 4) << 24);
 
-    // ---- 4 x 8 register tile: pixels w0 + 4wq + i, disparities 8dq + j
-    const int wq = tid & 7, dq = tid >> 3;
-    const int d0 = dq * 8;
-    const bool active = d0 < Dr;
-    float acc[4][8];
-#pragma unroll
-    for (int i = 0; i < 4; i++)
-#pragma unroll
-        for (int j = 0; j < 8; j++) acc[i][j] = 0.f;
-    if (active) {
-        const int ra = 4 * wq;                      // first left pixel (tile relative)
-        const int rb = 4 * wq - d0 + Dr - 7;        // first right pixel: (w - d) for i = 0, j = 7
-#pragma unroll 2
-        for (int c4 = 0; c4 < 16; c4++) {
-            float4 a[4], b[11];
-#pragma unroll
-            for (int i = 0; i < 4; i++) a[i] = As[swz(ra + i, c4)];
-#pragma unroll
-            for (int k = 0; k < 11; k++) b[k] = Bs[swz(rb + k, c4)];
-#pragma unroll
-            for (int i = 0; i < 4; i++)
-#pragma unroll
-                for (int j = 0; j < 8; j++) {
-                    const float4 y = b[i - j + 7];
-                    acc[i][j] = fmaf(a[i].x, y.x, acc[i][j]);
-                    acc[i][j] = fmaf(a[i].y, y.y, acc[i][j]);
-                    acc[i][j] = fmaf(a[i].z, y.z, acc[i][j]);
-                    acc[i][j] = fmaf(a[i].w, y.w, acc[i][j]);
+    if (warp < 4) {
+        // ================= front end: TMA, operand split, MMA issue =================
+        unsigned g = 0, ta = 0;
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ta++) {
+            const int h = tile / nwt, w0 = (tile - h * nwt) * CV_BM;
+            const int x_lo = w0 + CV_BM - CV_BN * nchunks;
+            for (int c = 0; c < nchunks; c++, g++) {
+                const unsigned buf = g & 1;
+                if (tid == 0) {
+                    // single-buffered operands: every MMA issued so far must have finished reading them
+                    if (g > 0) cv_mbar_wait(&sm.bar_full[(g - 1) & 1], ((g - 1) >> 1) & 1);
+                    if (c == 0) {
+                        cv_mbar_expect_tx(&sm.bar_tma_a, CV_TILE_BYTES);
+                        cv_tma_load_3d(sm.a_hi, &maps.fl, 0, w0, h, &sm.bar_tma_a);
+                        cv_tma_load_3d(sm.a_hi + CV_KB_BYTES, &maps.fl, 32, w0, h, &sm.bar_tma_a);
+                    }
+                    cv_mbar_expect_tx(&sm.bar_tma_b, CV_TILE_BYTES);
+                    cv_tma_load_3d(sm.b_hi, &maps.fr, 0, x_lo + CV_BN * c, h, &sm.bar_tma_b);
+                    cv_tma_load_3d(sm.b_hi + CV_KB_BYTES, &maps.fr, 32, x_lo + CV_BN * c, h, &sm.bar_tma_b);
                 }
-        }
-    }
-    __syncthreads();                                // everyone is done reading Bs
-
-    // ---- L straight from registers; the tile (negated, pf:111) also goes to shared memory for R
-    const int SP = Dr + 4;                          // row pitch of the output tile in floats
-    float *Ss = reinterpret_cast<float *>(Bs);
-    if (active) {
+                if (c == 0) {
+                    cv_mbar_wait(&sm.bar_tma_a, ta & 1);
+                    cv_split_tile(sm.a_hi, sm.a_lo, tid);
+                }
+                cv_mbar_wait(&sm.bar_tma_b, g & 1);
+                cv_split_tile(sm.b_hi, sm.b_lo, tid);
+                asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");   // operand writes -> tensor-core (async proxy) reads
+                cv_named_barrier(1, 128);
+                if (tid == 0) {
+                    if (g >= 2) cv_mbar_wait(&sm.bar_empty[buf], ((g >> 1) - 1) & 1);   // accumulator drained by the epilogue
+                    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+                    const unsigned d_tmem = tmem_base + buf * CV_BN;
+                    const unsigned long long ah = cv_smem_desc(cv_smem_u32(sm.a_hi)), al = cv_smem_desc(cv_smem_u32(sm.a_lo));
+                    const unsigned long long bh = cv_smem_desc(cv_smem_u32(sm.b_hi)), bl = cv_smem_desc(cv_smem_u32(sm.b_lo));
+                    unsigned acc = 0;
 #pragma unroll
-        for (int i = 0; i < 4; i++) {
-            const int w = w0 + 4 * wq + i;
-            float4 lo = make_float4(-acc[i][0], -acc[i][1], -acc[i][2], -acc[i][3]);
-            float4 hi = make_float4(-acc[i][4], -acc[i][5], -acc[i][6], -acc[i][7]);
-            float4 *srow = reinterpret_cast<float4 *>(Ss + (4 * wq + i) * SP + d0);
-            srow[0] = lo;
-            srow[1] = hi;
-            if (w < W) {
-                // cells with w < d are overwritten by k_cost_fill afterwards
-                float4 *lrow = reinterpret_cast<float4 *>(L + ((size_t)h * W + w) * Dp + d0);
-                if (d0 < Dp) lrow[0] = lo;
-                if (d0 + 4 < Dp) lrow[1] = hi;
+                    for (int kb = 0; kb < 2; kb++)
+#pragma unroll
+                        for (int ks = 0; ks < 4; ks++) {
+                            const unsigned long long off = (unsigned long long)((kb * CV_KB_BYTES + ks * 32) >> 4);
+                            cv_mma_tf32(d_tmem, ah + off, bh + off, idesc, acc);   // hi . hi
+                            acc = 1;
+                            cv_mma_tf32(d_tmem, ah + off, bl + off, idesc, 1);     // hi . lo
+                            cv_mma_tf32(d_tmem, al + off, bh + off, idesc, 1);     // lo . hi
+                        }
+                    cv_mma_commit(&sm.bar_full[buf]);
+                }
+            }
+        }
+    } else {
+        // ================= epilogue: TMEM -> R (direct), L (through the staging tile) =================
+        const int q = warp - 4;                       // TMEM lane quarter of this warp
+        const int m = 32 * q + lane;
+        unsigned g = 0;
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            const int h = tile / nwt, w0 = (tile - h * nwt) * CV_BM;
+            const int x_lo = w0 + CV_BM - CV_BN * nchunks;
+            const int w = w0 + m;
+            const size_t rowbase = (size_t)h * W;
+            for (int c = 0; c < nchunks; c++, g++) {
+                const unsigned buf = g & 1;
+                const int x0c = x_lo + CV_BN * c;
+                cv_mbar_wait(&sm.bar_full[buf], (g >> 1) & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+#pragma unroll 1
+                for (int grp = 0; grp < CV_BN / 32; grp++) {
+                    // d of (lane, column j) = dbase + lane - j; skip groups entirely outside [0, D)
+                    const int dbase = w0 + 32 * q - x0c - 32 * grp;
+                    if (dbase + 31 < 0 || dbase - 31 >= D) continue;
+                    unsigned v[32];
+                    cv_tmem_ld32(tmem_base + ((unsigned)(32 * q) << 16) + buf * CV_BN + grp * 32, v);
+                    float *ls = sm.ls + m * CV_LS_PITCH + (CV_BN - 1 - 32 * grp);
+#pragma unroll
+                    for (int j = 0; j < 32; j++) {
+                        const float val = -__uint_as_float(v[j]);                 // pf:111-112
+                        const int x = x0c + 32 * grp + j, d = dbase + lane - j;
+                        if (x >= 0 && x < W && w < W && d >= 0 && d < D) R[(rowbase + x) * Dp + d] = val;
+                        ls[-j] = val;
+                    }
+                }
+                asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+                cv_mbar_arrive(&sm.bar_empty[buf]);
+                cv_named_barrier(2, 128);
+                // L: pixel p of this warp's quarter owns d = dstart .. dstart + 127 of this chunk
+#pragma unroll 1
+                for (int p = 32 * q; p < 32 * q + 32; p++) {
+                    const int wp = w0 + p;
+                    if (wp >= W) break;
+                    const int dstart = wp - x0c - (CV_BN - 1);
+                    if (dstart + CV_BN <= 0 || dstart >= D) continue;
+                    float *dst = L + (rowbase + wp) * Dp;
+                    const float *src = sm.ls + p * CV_LS_PITCH;
+#pragma unroll
+                    for (int t = 0; t < CV_BN / 32; t++) {
+                        const int dd = dstart + 32 * t + lane;
+                        if (dd >= 0 && dd < D) dst[dd] = src[32 * t + lane];
+                    }
+                }
+                cv_named_barrier(2, 128);
             }
         }
     }
+    asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
     __syncthreads();
-
-    // ---- R[h][x][d] = S(x + d, d): one warp per right-image pixel x, lanes over the run of d whose
-    //      left pixel x + d lies in this tile
-    const int lane = tid & 31, warp = tid >> 5, nwarps = nthr >> 5;
-    const int wend = min(w0 + CV_TWB, W);           // exclusive
-    for (int x = max(w0 - (D - 1), 0) + warp; x < wend; x += nwarps) {
-        const int dlo = max(0, w0 - x);
-        const int dhi = min(D - 1, wend - 1 - x);
-        const int d = dlo + lane;
-        if (d <= dhi) R[((size_t)h * W + x) * Dp + d] = Ss[(x + d - w0) * SP + d];
-    }
+    if (warp == 0)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"(2 * CV_BN) : "memory");
 }
 
 // Invalid triangles (pf:94-95 for L, pf:105-106 for R), in the already negated domain (negation
@@ -164,6 +316,36 @@ __global__ void k_cost_fill(float *__restrict__ L, float *__restrict__ R, int H,
     }
 }
 
+
+typedef CUresult (*CvEncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                    const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static int cv_feature_map(CUtensorMap &map, const float *f, int H, int W) {
+    static CvEncodeTiledFn enc = nullptr;
+    if (!enc) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess ||
+            qres != cudaDriverEntryPointSuccess) {
+            set_error("cost_volume: cuTensorMapEncodeTiled is not available from this driver");
+            return MCCNN_ERR_CUDA;
+        }
+        enc = (CvEncodeTiledFn)p;
+    }
+    const cuuint64_t gdim[3] = {CV_C, (cuuint64_t)W, (cuuint64_t)H};
+    const cuuint64_t gstr[2] = {CV_C * 4, (cuuint64_t)W * CV_C * 4};
+    const cuuint32_t box[3] = {32, CV_BM, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void *)f, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cost_volume: cuTensorMapEncodeTiled failed (%d)", (int)r);
+        return MCCNN_ERR_CUDA;
+    }
+    return MCCNN_OK;
+}
+
 }  // namespace mccnn
 
 using namespace mccnn;
@@ -175,20 +357,31 @@ int mccnn_cost_volume(const float *fl, const float *fr, float *L, float *R, int 
     MCCNN_REQUIRE(C == CV_C, "cost_volume: %d feature channels unsupported (the network emits 64, model.py:38)", C);
     MCCNN_REQUIRE(H >= 1 && D >= 1 && W >= D + 2, "cost_volume: need W >= ndisp + 2 (pf:94-95), got W=%d ndisp=%d", W, D);
     MCCNN_REQUIRE(D <= 512, "cost_volume: ndisp %d too large (max 512)", D);
+    MCCNN_REQUIRE(((uintptr_t)fl & 15) == 0 && ((uintptr_t)fr & 15) == 0, "cost_volume: features must be 16-byte aligned");
     cudaStream_t s = (cudaStream_t)stream;
     const int Dp = dpitch(D);
-    const int Dr = ((D + 7) / 8) * 8;
-    int threads = ((8 * (Dr / 8) + 31) / 32) * 32;
-    if (threads < 64) threads = 64;
-    const size_t smem = (size_t)(CV_TWB + CV_TWB + Dr) * 16 * sizeof(float4);
-    static size_t smem_set = 0;
-    if (smem > smem_set) {
-        MCCNN_CUDA(cudaFuncSetAttribute(k_cost_volume, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        smem_set = smem;
+    CvMaps maps;
+    int rc = cv_feature_map(maps.fl, fl, H, W);
+    if (rc) return rc;
+    rc = cv_feature_map(maps.fr, fr, H, W);
+    if (rc) return rc;
+    static int num_sms = 0;
+    static bool smem_set = false;
+    if (num_sms == 0) {
+        int dev = 0;
+        MCCNN_CUDA(cudaGetDevice(&dev));
+        MCCNN_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
     }
-    dim3 grid(cdiv(W, CV_TWB), H);
-    k_cost_volume<<<grid, threads, smem, s>>>(fl, fr, L, R, H, W, D, Dp, Dr);
-    MCCNN_LAUNCHED("cost_volume");
+    if (!smem_set) {
+        MCCNN_CUDA(cudaFuncSetAttribute(k_cost_volume_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CvSmem)));
+        smem_set = true;
+    }
+    const int nwt = cdiv(W, CV_BM), nchunks = cdiv(CV_BM - 1 + D, CV_BN);
+    const long long ntiles = (long long)nwt * H;
+    MCCNN_REQUIRE(ntiles < (1ll << 31), "cost_volume: image too large");
+    const int grid = ntiles < num_sms ? (int)ntiles : num_sms;
+    k_cost_volume_tc<<<grid, CV_THREADS, sizeof(CvSmem), s>>>(maps, L, R, H, W, D, Dp, nwt, nchunks, (int)ntiles);
+    MCCNN_LAUNCHED("cost_volume_tc");
     if (D > 1) {
         dim3 fgrid(cdiv(cdiv(D, 32), 4), H);
         k_cost_fill<<<fgrid, 128, 0, s>>>(L, R, H, W, D, Dp);
