@@ -15,12 +15,14 @@
 //       which restores float32-level accuracy (error ~1e-6 of the volume's scale; plain TF32 would
 //       break the 1e-4 gate).  Accumulators are double buffered in TMEM so the
 //       next chunk is loaded, split and multiplied while the previous one is written out.
-//   epilogue (warps 4-7, one per TMEM lane quarter): tcgen05.ld 32 columns at a time.  A TMEM column
+//       Both S (lanes = left pixels) and S^T (lanes = right pixels) are formed -- the tensor pipe is
+//       far from busy -- so that neither volume needs a transpose on the way out; the negation
+//       (pf:111-112) is the descriptor's negate-A bit.
+//   epilogue (warps 4-7, one per TMEM lane quarter): tcgen05.ld 32 columns at a time.  A column of S
 //       is one right pixel x and the 32 lanes of a warp are consecutive left pixels w, i.e.
 //       consecutive d = w - x: R[h][x][d..d+31] is one coalesced 128-byte store straight from
-//       registers.  L[h][w][.] needs the transpose: values go through a padded shared-memory tile
-//       and leave as 128-byte runs of consecutive d per pixel.  Column groups whose d range lies
-//       outside [0, ndisp) are skipped.  The negation (pf:111-112) is folded into the stores.
+//       registers; S^T gives L[h][w][d..d-31] the same way.  Column groups whose d range lies
+//       outside [0, ndisp) are skipped.
 // k_cost_fill then overwrites the cells that have no correspondent.
 #include <cuda.h>
 #include "common.cuh"
@@ -28,17 +30,17 @@
 namespace mccnn {
 
 constexpr int CV_C = 64;                   // feature channels (model.py:38)
-constexpr int CV_BM = 128;                 // left pixels per tile (MMA M, TMEM lanes)
-constexpr int CV_BN = 128;                 // right pixels per chunk (MMA N, TMEM columns)
+constexpr int CV_BM = 128;                 // left pixels per tile
+constexpr int CV_BN = 128;                 // right pixels per chunk
 constexpr int CV_KB_BYTES = 128 * 128;     // one K block: 128 rows x 32 floats, 128B-swizzled
 constexpr int CV_TILE_BYTES = 2 * CV_KB_BYTES;
-constexpr int CV_LS_PITCH = CV_BN + 1;     // staging tile pitch (floats): conflict-free transposed writes
 constexpr int CV_THREADS = 256;
+constexpr int CV_TMEM_COLS = 512;          // 2 buffers x (S: lanes = left pixels | S^T: lanes = right pixels)
 
 struct __align__(1024) CvSmem {
-    unsigned char a_hi[CV_TILE_BYTES], a_lo[CV_TILE_BYTES], b_hi[CV_TILE_BYTES], b_lo[CV_TILE_BYTES];
-    float ls[CV_BM * CV_LS_PITCH];
-    unsigned long long bar_tma_a, bar_tma_b, bar_full[2], bar_empty[2];
+    unsigned char a_hi[CV_TILE_BYTES], a_lo[CV_TILE_BYTES];            // left tile, split
+    unsigned char b_hi[2][CV_TILE_BYTES], b_lo[2][CV_TILE_BYTES];      // right chunks, split, double buffered
+    unsigned long long bar_tma_a, bar_tma_b[2], bar_full[2], bar_empty[2];
     unsigned tmem_base;
 };
 
@@ -87,7 +89,7 @@ __device__ __forceinline__ unsigned long long cv_smem_desc(unsigned smem_addr) {
     d |= (unsigned long long)2 << 61;                     // SWIZZLE_128B
     return d;
 }
-// D[tmem] (+)= A[smem] . B[smem]^T, M = 128, N = 128, K = 8 (tf32)
+// D[tmem] (+)= -A[smem] . B[smem]^T, M = 128, N = 128, K = 8 (tf32)
 __device__ __forceinline__ void cv_mma_tf32(unsigned tmem_d, unsigned long long a_desc, unsigned long long b_desc,
                                             unsigned idesc, unsigned accumulate) {
     asm volatile(
@@ -117,11 +119,11 @@ __device__ __forceinline__ void cv_tmem_ld32(unsigned taddr, unsigned (&v)[32]) 
 }
 
 // hi = tf32(x) in place, lo = x - hi (exact) at the same offset of `lo` (the swizzle permutes 16-byte chunks only)
-__device__ __forceinline__ void cv_split_tile(unsigned char *hi, unsigned char *lo, int ftid) {
+__device__ __forceinline__ void cv_split_tile(unsigned char *hi, unsigned char *lo, int ftid, int nthr) {
     float4 *h4 = reinterpret_cast<float4 *>(hi);
     float4 *l4 = reinterpret_cast<float4 *>(lo);
 #pragma unroll 4
-    for (int i = ftid; i < CV_TILE_BYTES / 16; i += 128) {
+    for (int i = ftid; i < CV_TILE_BYTES / 16; i += nthr) {
         const float4 x = h4[i];
         unsigned a, b, c, d;
         asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(a) : "f"(x.x));
@@ -134,6 +136,41 @@ __device__ __forceinline__ void cv_split_tile(unsigned char *hi, unsigned char *
     }
 }
 
+// One warp writes its 32 TMEM lanes x 128 columns of an accumulator to a volume.  Column n is pixel pix0 + n;
+// lane l holds disparity d0 + dl*l + dn*n with (dl, dn) = (+1, -1) for R (lanes = left pixels) and (-1, +1)
+// for L (lanes = right pixels): the 32 lanes of one column are 32 consecutive disparities of one pixel,
+// i.e. one coalesced 128-byte store.  lane_ok masks lanes whose own pixel lies outside the image.
+template <int DL>
+__device__ __forceinline__ void cv_store_quarter(float *__restrict__ vol, unsigned taddr, size_t rowbase, int pix0, int d0,
+                                                 bool lane_ok, int W, int D, int Dp) {
+    constexpr int DN = -DL;
+    const int lane = threadIdx.x & 31;
+#pragma unroll 1
+    for (int grp = 0; grp < CV_BN / 32; grp++) {
+        const int n0 = 32 * grp;
+        const int dc = d0 + DN * n0;                            // d at (lane 0, column n0); the group spans dc - 31 .. dc + 31
+        if (dc + 31 < 0 || dc - 31 >= D) continue;              // (warp uniform)
+        if (pix0 + n0 >= W || pix0 + n0 + 31 < 0) continue;
+        unsigned v[32];
+        cv_tmem_ld32(taddr + n0, v);
+        const int dl = dc + DL * lane;                          // this lane's d at column n0
+        float *p = vol + ((ptrdiff_t)rowbase + pix0 + n0) * (ptrdiff_t)Dp + dl;
+        const bool interior = dc - 31 >= 0 && dc + 31 < D && pix0 + n0 >= 0 && pix0 + n0 + 31 < W &&
+                              __all_sync(0xffffffffu, lane_ok);
+        if (interior) {
+#pragma unroll
+            for (int j = 0; j < 32; j++) p[(ptrdiff_t)j * (Dp + DN)] = __uint_as_float(v[j]);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 32; j++) {
+                const int d = dl + DN * j, pix = pix0 + n0 + j;
+                if (lane_ok && (unsigned)d < (unsigned)D && (unsigned)pix < (unsigned)W)
+                    p[(ptrdiff_t)j * (Dp + DN)] = __uint_as_float(v[j]);
+            }
+        }
+    }
+}
+
 __global__ void __launch_bounds__(CV_THREADS, 1)
 k_cost_volume_tc(const __grid_constant__ CvMaps maps, float *__restrict__ L, float *__restrict__ R, int H, int W, int D,
                  int Dp, int nwt, int nchunks, int ntiles) {
@@ -143,13 +180,14 @@ k_cost_volume_tc(const __grid_constant__ CvMaps maps, float *__restrict__ L, flo
 
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(cv_smem_u32(&sm.tmem_base)),
-                     "r"(2 * CV_BN)
+                     "r"(CV_TMEM_COLS)
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
     }
     if (tid == 32) {
         cv_mbar_init(&sm.bar_tma_a, 1);
-        cv_mbar_init(&sm.bar_tma_b, 1);
+        cv_mbar_init(&sm.bar_tma_b[0], 1);
+        cv_mbar_init(&sm.bar_tma_b[1], 1);
         cv_mbar_init(&sm.bar_full[0], 1);
         cv_mbar_init(&sm.bar_full[1], 1);
         cv_mbar_init(&sm.bar_empty[0], 128);
@@ -160,115 +198,100 @@ k_cost_volume_tc(const __grid_constant__ CvMaps maps, float *__restrict__ L, flo
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
     const unsigned tmem_base = sm.tmem_base;
-    // instruction descriptor: D = F32, A = B = TF32, both K-major, N = 128, M = 128
-    const unsigned idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((unsigned)(CV_BN >> 3) << 17) | ((unsigned)(CV_BM >> 4) << 24);
+    // instruction descriptor: D = F32, A = B = TF32, A negated (pf:111-112), both K-major, N = 128, M = 128
+    const unsigned idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 13) | ((unsigned)(CV_BN >> 3) << 17) |
+                           ((unsigned)(CV_BM >> 4) << 24);
 
     if (warp < 4) {
         // ================= front end: TMA, operand split, MMA issue =================
+        // warp 0 only drives (TMA + MMA issue by its lane 0); warps 1-3 split the operands
+        auto issue_b = [&](int tile, int c, unsigned g) {
+            const int h = tile / nwt, w0 = (tile - h * nwt) * CV_BM;
+            const int x0c = w0 + CV_BM - CV_BN * nchunks + CV_BN * c;
+            unsigned char *dst = sm.b_hi[g & 1];
+            cv_mbar_expect_tx(&sm.bar_tma_b[g & 1], CV_TILE_BYTES);
+            cv_tma_load_3d(dst, &maps.fr, 0, x0c, h, &sm.bar_tma_b[g & 1]);
+            cv_tma_load_3d(dst + CV_KB_BYTES, &maps.fr, 32, x0c, h, &sm.bar_tma_b[g & 1]);
+        };
         unsigned g = 0, ta = 0;
+        if (tid == 0 && (int)blockIdx.x < ntiles) issue_b(blockIdx.x, 0, 0);
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ta++) {
             const int h = tile / nwt, w0 = (tile - h * nwt) * CV_BM;
-            const int x_lo = w0 + CV_BM - CV_BN * nchunks;
             for (int c = 0; c < nchunks; c++, g++) {
                 const unsigned buf = g & 1;
                 if (tid == 0) {
-                    // single-buffered operands: every MMA issued so far must have finished reading them
+                    // MMAs of chunk g-1 done: its B buffer (the one chunk g+1 lands in) and, at a tile start, A are free
                     if (g > 0) cv_mbar_wait(&sm.bar_full[(g - 1) & 1], ((g - 1) >> 1) & 1);
                     if (c == 0) {
                         cv_mbar_expect_tx(&sm.bar_tma_a, CV_TILE_BYTES);
                         cv_tma_load_3d(sm.a_hi, &maps.fl, 0, w0, h, &sm.bar_tma_a);
                         cv_tma_load_3d(sm.a_hi + CV_KB_BYTES, &maps.fl, 32, w0, h, &sm.bar_tma_a);
                     }
-                    cv_mbar_expect_tx(&sm.bar_tma_b, CV_TILE_BYTES);
-                    cv_tma_load_3d(sm.b_hi, &maps.fr, 0, x_lo + CV_BN * c, h, &sm.bar_tma_b);
-                    cv_tma_load_3d(sm.b_hi + CV_KB_BYTES, &maps.fr, 32, x_lo + CV_BN * c, h, &sm.bar_tma_b);
+                    if (c + 1 < nchunks) issue_b(tile, c + 1, g + 1);
+                    else if (tile + (int)gridDim.x < ntiles) issue_b(tile + gridDim.x, 0, g + 1);
                 }
-                if (c == 0) {
-                    cv_mbar_wait(&sm.bar_tma_a, ta & 1);
-                    cv_split_tile(sm.a_hi, sm.a_lo, tid);
+                if (warp > 0) {
+                    if (c == 0) {
+                        cv_mbar_wait(&sm.bar_tma_a, ta & 1);
+                        cv_split_tile(sm.a_hi, sm.a_lo, tid - 32, 96);
+                    }
+                    cv_mbar_wait(&sm.bar_tma_b[buf], (g >> 1) & 1);
+                    cv_split_tile(sm.b_hi[buf], sm.b_lo[buf], tid - 32, 96);
+                    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");   // operand writes -> tensor-core reads
                 }
-                cv_mbar_wait(&sm.bar_tma_b, g & 1);
-                cv_split_tile(sm.b_hi, sm.b_lo, tid);
-                asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");   // operand writes -> tensor-core (async proxy) reads
                 cv_named_barrier(1, 128);
                 if (tid == 0) {
-                    if (g >= 2) cv_mbar_wait(&sm.bar_empty[buf], ((g >> 1) - 1) & 1);   // accumulator drained by the epilogue
+                    if (g >= 2) cv_mbar_wait(&sm.bar_empty[buf], ((g >> 1) - 1) & 1);   // accumulators drained by the epilogue
                     asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-                    const unsigned d_tmem = tmem_base + buf * CV_BN;
+                    const unsigned d_s = tmem_base + buf * (2 * CV_BN), d_t = d_s + CV_BN;
                     const unsigned long long ah = cv_smem_desc(cv_smem_u32(sm.a_hi)), al = cv_smem_desc(cv_smem_u32(sm.a_lo));
-                    const unsigned long long bh = cv_smem_desc(cv_smem_u32(sm.b_hi)), bl = cv_smem_desc(cv_smem_u32(sm.b_lo));
+                    const unsigned long long bh = cv_smem_desc(cv_smem_u32(sm.b_hi[buf])), bl = cv_smem_desc(cv_smem_u32(sm.b_lo[buf]));
                     unsigned acc = 0;
 #pragma unroll
                     for (int kb = 0; kb < 2; kb++)
 #pragma unroll
                         for (int ks = 0; ks < 4; ks++) {
                             const unsigned long long off = (unsigned long long)((kb * CV_KB_BYTES + ks * 32) >> 4);
-                            cv_mma_tf32(d_tmem, ah + off, bh + off, idesc, acc);   // hi . hi
+                            // S = -FL.FR^T (lanes = left pixels) and S^T (lanes = right pixels), each hi.hi + hi.lo + lo.hi
+                            cv_mma_tf32(d_s, ah + off, bh + off, idesc, acc);
+                            cv_mma_tf32(d_t, bh + off, ah + off, idesc, acc);
                             acc = 1;
-                            cv_mma_tf32(d_tmem, ah + off, bl + off, idesc, 1);     // hi . lo
-                            cv_mma_tf32(d_tmem, al + off, bh + off, idesc, 1);     // lo . hi
+                            cv_mma_tf32(d_s, ah + off, bl + off, idesc, 1);
+                            cv_mma_tf32(d_t, bh + off, al + off, idesc, 1);
+                            cv_mma_tf32(d_s, al + off, bh + off, idesc, 1);
+                            cv_mma_tf32(d_t, bl + off, ah + off, idesc, 1);
                         }
                     cv_mma_commit(&sm.bar_full[buf]);
                 }
             }
         }
     } else {
-        // ================= epilogue: TMEM -> R (direct), L (through the staging tile) =================
-        const int q = warp - 4;                       // TMEM lane quarter of this warp
-        const int m = 32 * q + lane;
+        // ================= epilogue: TMEM -> R and L, one warp per TMEM lane quarter =================
+        const int q = warp - 4;
         unsigned g = 0;
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
             const int h = tile / nwt, w0 = (tile - h * nwt) * CV_BM;
             const int x_lo = w0 + CV_BM - CV_BN * nchunks;
-            const int w = w0 + m;
             const size_t rowbase = (size_t)h * W;
             for (int c = 0; c < nchunks; c++, g++) {
                 const unsigned buf = g & 1;
                 const int x0c = x_lo + CV_BN * c;
                 cv_mbar_wait(&sm.bar_full[buf], (g >> 1) & 1);
                 asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-#pragma unroll 1
-                for (int grp = 0; grp < CV_BN / 32; grp++) {
-                    // d of (lane, column j) = dbase + lane - j; skip groups entirely outside [0, D)
-                    const int dbase = w0 + 32 * q - x0c - 32 * grp;
-                    if (dbase + 31 < 0 || dbase - 31 >= D) continue;
-                    unsigned v[32];
-                    cv_tmem_ld32(tmem_base + ((unsigned)(32 * q) << 16) + buf * CV_BN + grp * 32, v);
-                    float *ls = sm.ls + m * CV_LS_PITCH + (CV_BN - 1 - 32 * grp);
-#pragma unroll
-                    for (int j = 0; j < 32; j++) {
-                        const float val = -__uint_as_float(v[j]);                 // pf:111-112
-                        const int x = x0c + 32 * grp + j, d = dbase + lane - j;
-                        if (x >= 0 && x < W && w < W && d >= 0 && d < D) R[(rowbase + x) * Dp + d] = val;
-                        ls[-j] = val;
-                    }
-                }
+                const unsigned t_s = tmem_base + ((unsigned)(32 * q) << 16) + buf * (2 * CV_BN), t_t = t_s + CV_BN;
+                // R[h][x][d]: lanes are left pixels w = w0 + 32q + lane, columns right pixels x = x0c + n, d = w - x
+                cv_store_quarter<+1>(R, t_s, rowbase, x0c, w0 + 32 * q - x0c, w0 + 32 * q + lane < W, W, D, Dp);
+                // L[h][w][d]: lanes are right pixels x = x0c + 32q + lane, columns left pixels w = w0 + n, d = w - x
+                cv_store_quarter<-1>(L, t_t, rowbase, w0, w0 - x0c - 32 * q, true, W, D, Dp);
                 asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
                 cv_mbar_arrive(&sm.bar_empty[buf]);
-                cv_named_barrier(2, 128);
-                // L: pixel p of this warp's quarter owns d = dstart .. dstart + 127 of this chunk
-#pragma unroll 1
-                for (int p = 32 * q; p < 32 * q + 32; p++) {
-                    const int wp = w0 + p;
-                    if (wp >= W) break;
-                    const int dstart = wp - x0c - (CV_BN - 1);
-                    if (dstart + CV_BN <= 0 || dstart >= D) continue;
-                    float *dst = L + (rowbase + wp) * Dp;
-                    const float *src = sm.ls + p * CV_LS_PITCH;
-#pragma unroll
-                    for (int t = 0; t < CV_BN / 32; t++) {
-                        const int dd = dstart + 32 * t + lane;
-                        if (dd >= 0 && dd < D) dst[dd] = src[32 * t + lane];
-                    }
-                }
-                cv_named_barrier(2, 128);
             }
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
     __syncthreads();
     if (warp == 0)
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"(2 * CV_BN) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"(CV_TMEM_COLS) : "memory");
 }
 
 // Invalid triangles (pf:94-95 for L, pf:105-106 for R), in the already negated domain (negation
