@@ -34,11 +34,13 @@ constexpr int CV_BM = 128;                 // left pixels per tile
 constexpr int CV_BN = 128;                 // right pixels per chunk
 constexpr int CV_KB_BYTES = 128 * 128;     // one K block: 128 rows x 32 floats, 128B-swizzled
 constexpr int CV_TILE_BYTES = 2 * CV_KB_BYTES;
-constexpr int CV_THREADS = 256;
+constexpr int CV_THREADS = 512;            // warp 0: MMA issue, warp 1: TMA, warps 2-7: operand split, 8-11: R, 12-15: L
+constexpr int CV_NSPLIT = 192;             // splitter threads (warps 2-7)
 constexpr int CV_TMEM_COLS = 512;          // 2 buffers x (S: lanes = left pixels | S^T: lanes = right pixels)
 
 struct __align__(1024) CvSmem {
     unsigned char a_hi[CV_TILE_BYTES], a_lo[CV_TILE_BYTES];            // left tile, split
+    unsigned char a_raw[CV_TILE_BYTES];                                // next left tile as loaded (prefetch)
     unsigned char b_hi[2][CV_TILE_BYTES], b_lo[2][CV_TILE_BYTES];      // right chunks, split, double buffered
     unsigned long long bar_tma_a, bar_tma_b[2], bar_full[2], bar_empty[2];
     unsigned tmem_base;
@@ -118,13 +120,15 @@ __device__ __forceinline__ void cv_tmem_ld32(unsigned taddr, unsigned (&v)[32]) 
     asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
 }
 
-// hi = tf32(x) in place, lo = x - hi (exact) at the same offset of `lo` (the swizzle permutes 16-byte chunks only)
-__device__ __forceinline__ void cv_split_tile(unsigned char *hi, unsigned char *lo, int ftid, int nthr) {
+// hi = tf32(x), lo = x - hi (exact), both at the offset x has in `raw` (the swizzle permutes 16-byte chunks only)
+__device__ __forceinline__ void cv_split_tile(const unsigned char *raw, unsigned char *hi, unsigned char *lo, int ftid,
+                                              int nthr) {
+    const float4 *r4 = reinterpret_cast<const float4 *>(raw);
     float4 *h4 = reinterpret_cast<float4 *>(hi);
     float4 *l4 = reinterpret_cast<float4 *>(lo);
 #pragma unroll 4
     for (int i = ftid; i < CV_TILE_BYTES / 16; i += nthr) {
-        const float4 x = h4[i];
+        const float4 x = r4[i];
         unsigned a, b, c, d;
         asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(a) : "f"(x.x));
         asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(b) : "f"(x.y));
@@ -190,8 +194,8 @@ k_cost_volume_tc(const __grid_constant__ CvMaps maps, float *__restrict__ L, flo
         cv_mbar_init(&sm.bar_tma_b[1], 1);
         cv_mbar_init(&sm.bar_full[0], 1);
         cv_mbar_init(&sm.bar_full[1], 1);
-        cv_mbar_init(&sm.bar_empty[0], 128);
-        cv_mbar_init(&sm.bar_empty[1], 128);
+        cv_mbar_init(&sm.bar_empty[0], 256);
+        cv_mbar_init(&sm.bar_empty[1], 256);
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
@@ -202,44 +206,62 @@ k_cost_volume_tc(const __grid_constant__ CvMaps maps, float *__restrict__ L, flo
     const unsigned idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 13) | ((unsigned)(CV_BN >> 3) << 17) |
                            ((unsigned)(CV_BM >> 4) << 24);
 
-    if (warp < 4) {
-        // ================= front end: TMA, operand split, MMA issue =================
-        // warp 0 only drives (TMA + MMA issue by its lane 0); warps 1-3 split the operands
-        auto issue_b = [&](int tile, int c, unsigned g) {
-            const int h = tile / nwt, w0 = (tile - h * nwt) * CV_BM;
-            const int x0c = w0 + CV_BM - CV_BN * nchunks + CV_BN * c;
-            unsigned char *dst = sm.b_hi[g & 1];
-            cv_mbar_expect_tx(&sm.bar_tma_b[g & 1], CV_TILE_BYTES);
-            cv_tma_load_3d(dst, &maps.fr, 0, x0c, h, &sm.bar_tma_b[g & 1]);
-            cv_tma_load_3d(dst + CV_KB_BYTES, &maps.fr, 32, x0c, h, &sm.bar_tma_b[g & 1]);
-        };
-        unsigned g = 0, ta = 0;
-        if (tid == 0 && (int)blockIdx.x < ntiles) issue_b(blockIdx.x, 0, 0);
-        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ta++) {
-            const int h = tile / nwt, w0 = (tile - h * nwt) * CV_BM;
-            for (int c = 0; c < nchunks; c++, g++) {
-                const unsigned buf = g & 1;
-                if (tid == 0) {
-                    // MMAs of chunk g-1 done: its B buffer (the one chunk g+1 lands in) and, at a tile start, A are free
-                    if (g > 0) cv_mbar_wait(&sm.bar_full[(g - 1) & 1], ((g - 1) >> 1) & 1);
-                    if (c == 0) {
-                        cv_mbar_expect_tx(&sm.bar_tma_a, CV_TILE_BYTES);
-                        cv_tma_load_3d(sm.a_hi, &maps.fl, 0, w0, h, &sm.bar_tma_a);
-                        cv_tma_load_3d(sm.a_hi + CV_KB_BYTES, &maps.fl, 32, w0, h, &sm.bar_tma_a);
+    if (warp == 1) {
+        // ================= TMA producer (one lane) =================
+        if (lane == 0) {
+            auto issue_b = [&](int tile, int c, unsigned g) {
+                const int h = tile / nwt, w0 = (tile - h * nwt) * CV_BM;
+                const int x0c = w0 + CV_BM - CV_BN * nchunks + CV_BN * c;
+                unsigned char *dst = sm.b_hi[g & 1];
+                cv_mbar_expect_tx(&sm.bar_tma_b[g & 1], CV_TILE_BYTES);
+                cv_tma_load_3d(dst, &maps.fr, 0, x0c, h, &sm.bar_tma_b[g & 1]);
+                cv_tma_load_3d(dst + CV_KB_BYTES, &maps.fr, 32, x0c, h, &sm.bar_tma_b[g & 1]);
+            };
+            auto issue_a = [&](int tile) {
+                const int h = tile / nwt, w0 = (tile - h * nwt) * CV_BM;
+                cv_mbar_expect_tx(&sm.bar_tma_a, CV_TILE_BYTES);
+                cv_tma_load_3d(sm.a_raw, &maps.fl, 0, w0, h, &sm.bar_tma_a);
+                cv_tma_load_3d(sm.a_raw + CV_KB_BYTES, &maps.fl, 32, w0, h, &sm.bar_tma_a);
+            };
+            unsigned g = 0;
+            if ((int)blockIdx.x < ntiles) {
+                issue_a(blockIdx.x);
+                issue_b(blockIdx.x, 0, 0);
+            }
+            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+                for (int c = 0; c < nchunks; c++, g++) {
+                    // chunk g+1 lands in the buffer chunk g-1 used: wait until the MMAs of g-1 are done with it.
+                    if (g > 0) {
+                        cv_mbar_wait(&sm.bar_full[(g - 1) & 1], ((g - 1) >> 1) & 1);
+                        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+                        // chunk g-1 opened a tile <=> c == 1 (or nchunks == 1): its split has consumed a_raw
+                        const bool opened = (nchunks == 1) ? true : (c == 1);
+                        const int opened_tile = (nchunks == 1) ? tile - (int)gridDim.x : tile;
+                        if (opened && opened_tile + (int)gridDim.x < ntiles) issue_a(opened_tile + gridDim.x);
                     }
                     if (c + 1 < nchunks) issue_b(tile, c + 1, g + 1);
                     else if (tile + (int)gridDim.x < ntiles) issue_b(tile + gridDim.x, 0, g + 1);
                 }
-                if (warp > 0) {
+            }
+        }
+    } else if (warp < 8) {
+        // ================= operand split (warps 2-7) and MMA issue (warp 0, lane 0) =================
+        unsigned g = 0, ta = 0;
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ta++) {
+            for (int c = 0; c < nchunks; c++, g++) {
+                const unsigned buf = g & 1;
+                if (warp >= 2) {
                     if (c == 0) {
+                        // the previous tile's MMAs no longer read a_hi / a_lo; the new tile was prefetched into a_raw
+                        if (g > 0) cv_mbar_wait(&sm.bar_full[(g - 1) & 1], ((g - 1) >> 1) & 1);
                         cv_mbar_wait(&sm.bar_tma_a, ta & 1);
-                        cv_split_tile(sm.a_hi, sm.a_lo, tid - 32, 96);
+                        cv_split_tile(sm.a_raw, sm.a_hi, sm.a_lo, tid - 64, CV_NSPLIT);
                     }
                     cv_mbar_wait(&sm.bar_tma_b[buf], (g >> 1) & 1);
-                    cv_split_tile(sm.b_hi[buf], sm.b_lo[buf], tid - 32, 96);
-                    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");   // operand writes -> tensor-core reads
+                    cv_split_tile(sm.b_hi[buf], sm.b_hi[buf], sm.b_lo[buf], tid - 64, CV_NSPLIT);
+                    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");   // operand accesses -> async proxy
                 }
-                cv_named_barrier(1, 128);
+                cv_named_barrier(1, 32 + CV_NSPLIT);
                 if (tid == 0) {
                     if (g >= 2) cv_mbar_wait(&sm.bar_empty[buf], ((g >> 1) - 1) & 1);   // accumulators drained by the epilogue
                     asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
@@ -267,7 +289,8 @@ k_cost_volume_tc(const __grid_constant__ CvMaps maps, float *__restrict__ L, flo
         }
     } else {
         // ================= epilogue: TMEM -> R and L, one warp per TMEM lane quarter =================
-        const int q = warp - 4;
+        const int q = warp & 3;                       // TMEM lane quarter this warp may read
+        const bool does_l = warp >= 12;               // warps 8-11 write R from S, warps 12-15 write L from S^T
         unsigned g = 0;
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
             const int h = tile / nwt, w0 = (tile - h * nwt) * CV_BM;
@@ -279,10 +302,13 @@ k_cost_volume_tc(const __grid_constant__ CvMaps maps, float *__restrict__ L, flo
                 cv_mbar_wait(&sm.bar_full[buf], (g >> 1) & 1);
                 asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
                 const unsigned t_s = tmem_base + ((unsigned)(32 * q) << 16) + buf * (2 * CV_BN), t_t = t_s + CV_BN;
-                // R[h][x][d]: lanes are left pixels w = w0 + 32q + lane, columns right pixels x = x0c + n, d = w - x
-                cv_store_quarter<+1>(R, t_s, rowbase, x0c, w0 + 32 * q - x0c, w0 + 32 * q + lane < W, W, D, Dp);
-                // L[h][w][d]: lanes are right pixels x = x0c + 32q + lane, columns left pixels w = w0 + n, d = w - x
-                cv_store_quarter<-1>(L, t_t, rowbase, w0, w0 - x0c - 32 * q, true, W, D, Dp);
+                if (!does_l) {
+                    // R[h][x][d]: lanes are left pixels w = w0 + 32q + lane, columns right pixels x = x0c + n, d = w - x
+                    cv_store_quarter<+1>(R, t_s, rowbase, x0c, w0 + 32 * q - x0c, w0 + 32 * q + lane < W, W, D, Dp);
+                } else {
+                    // L[h][w][d]: lanes are right pixels x = x0c + 32q + lane, columns left pixels w = w0 + n, d = w - x
+                    cv_store_quarter<-1>(L, t_t, rowbase, w0, w0 - x0c - 32 * q, true, W, D, Dp);
+                }
                 asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
                 cv_mbar_arrive(&sm.bar_empty[buf]);
             }
@@ -307,38 +333,33 @@ __global__ void k_cost_fill(float *__restrict__ L, float *__restrict__ R, int H,
     const int dmax = min(d0 + 31, D - 1);
     float *Lrow = L + (size_t)h * W * Dp;
     float *Rrow = R + (size_t)h * W * Dp;
-    {   // L: columns d-1 .. 0, right to left
-        float v1 = 0.f, v2 = 0.f, v3 = 0.f;          // values at c+1, c+2, c+3
-        for (int c = dmax - 1; c >= 0; c--) {
-            if (live && c == d - 1) {
-                v1 = Lrow[(size_t)(c + 1) * Dp + d];
-                v2 = Lrow[(size_t)(c + 2) * Dp + d];
-                v3 = Lrow[(size_t)(c + 3) * Dp + d];
-            }
-            if (live && c <= d - 1) {
-                float v = ((v1 + v2) + v3) / 3.0f;
-                Lrow[(size_t)c * Dp + d] = v;
-                v3 = v2; v2 = v1; v1 = v;
-            }
+    // the three valid cells each recurrence starts from (W >= D + 2 keeps them inside the row): all loads first
+    float l1 = 0.f, l2 = 0.f, l3 = 0.f, r1 = 0.f, r2 = 0.f, r3 = 0.f;
+    if (live) {
+        l1 = Lrow[(size_t)d * Dp + d];                          // columns d, d+1, d+2
+        l2 = Lrow[(size_t)(d + 1) * Dp + d];
+        l3 = Lrow[(size_t)(d + 2) * Dp + d];
+        r1 = Rrow[(size_t)(W - d - 1) * Dp + d];                // columns W-d-1, W-d-2, W-d-3
+        r2 = Rrow[(size_t)(W - d - 2) * Dp + d];
+        r3 = Rrow[(size_t)(W - d - 3) * Dp + d];
+    }
+    // L: columns d-1 .. 0, right to left (pf:94-95); lanes over d so that each step writes a contiguous run
+    for (int c = dmax - 1; c >= 0; c--) {
+        if (live && c <= d - 1) {
+            const float v = ((l1 + l2) + l3) / 3.0f;
+            Lrow[(size_t)c * Dp + d] = v;
+            l3 = l2; l2 = l1; l1 = v;
         }
     }
-    {   // R: columns W-d .. W-1, left to right
-        float v1 = 0.f, v2 = 0.f, v3 = 0.f;          // values at c-1, c-2, c-3
-        for (int c = W - dmax; c < W; c++) {
-            if (live && c == W - d) {
-                v1 = Rrow[(size_t)(c - 1) * Dp + d];
-                v2 = Rrow[(size_t)(c - 2) * Dp + d];
-                v3 = Rrow[(size_t)(c - 3) * Dp + d];
-            }
-            if (live && c >= W - d) {
-                float v = ((v3 + v2) + v1) / 3.0f;
-                Rrow[(size_t)c * Dp + d] = v;
-                v3 = v2; v2 = v1; v1 = v;
-            }
+    // R: columns W-d .. W-1, left to right (pf:105-106)
+    for (int c = W - dmax; c < W; c++) {
+        if (live && c >= W - d) {
+            const float v = ((r3 + r2) + r1) / 3.0f;
+            Rrow[(size_t)c * Dp + d] = v;
+            r3 = r2; r2 = r1; r1 = v;
         }
     }
 }
-
 
 typedef CUresult (*CvEncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                     const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
