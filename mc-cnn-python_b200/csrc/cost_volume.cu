@@ -24,8 +24,7 @@
 //       registers; S^T gives L[h][w][d..d-31] the same way.  Column groups whose d range lies
 //       outside [0, ndisp) are skipped.
 // k_cost_fill then overwrites the cells that have no correspondent.
-#include <cuda.h>
-#include "common.cuh"
+#include "tc_common.cuh"
 
 namespace mccnn {
 
@@ -48,98 +47,6 @@ struct __align__(1024) CvSmem {
 
 struct CvMaps { CUtensorMap fl, fr; };      // [H][W][64] float32, box {32 channels, 128 pixels, 1 row}, SWIZZLE_128B
 
-__device__ __forceinline__ unsigned cv_smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void cv_mbar_init(unsigned long long *bar, unsigned count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(cv_smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void cv_mbar_expect_tx(unsigned long long *bar, unsigned bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(cv_smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void cv_mbar_arrive(unsigned long long *bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(cv_smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void cv_mbar_wait(unsigned long long *bar, unsigned parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "CV_WAIT_%=:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, 0x989680;\n"
-        "@p bra CV_DONE_%=;\n"
-        "bra CV_WAIT_%=;\n"
-        "CV_DONE_%=:\n"
-        "}\n" ::"r"(cv_smem_u32(bar)), "r"(parity)
-        : "memory");
-}
-__device__ __forceinline__ void cv_tma_load_3d(void *smem_dst, const CUtensorMap *map, int c0, int c1, int c2,
-                                               unsigned long long *bar) {
-    asm volatile(
-        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];\n" ::
-            "r"(cv_smem_u32(smem_dst)), "l"(reinterpret_cast<unsigned long long>(map)), "r"(c0), "r"(c1), "r"(c2),
-        "r"(cv_smem_u32(bar))
-        : "memory");
-}
-__device__ __forceinline__ void cv_named_barrier(int id, int nthreads) {
-    asm volatile("bar.sync %0, %1;\n" ::"r"(id), "r"(nthreads) : "memory");
-}
-// K-major, 128B-swizzled operand: rows of 128 bytes, 8-row groups 1024 bytes apart
-__device__ __forceinline__ unsigned long long cv_smem_desc(unsigned smem_addr) {
-    unsigned long long d = 0;
-    d |= (unsigned long long)((smem_addr >> 4) & 0x3fff);
-    d |= (unsigned long long)1 << 16;                     // leading byte offset (unused for swizzled K-major)
-    d |= (unsigned long long)(1024 >> 4) << 32;           // stride byte offset between 8-row groups
-    d |= (unsigned long long)1 << 46;                     // descriptor version (sm_100)
-    d |= (unsigned long long)2 << 61;                     // SWIZZLE_128B
-    return d;
-}
-// D[tmem] (+)= -A[smem] . B[smem]^T, M = 128, N = 128, K = 8 (tf32)
-__device__ __forceinline__ void cv_mma_tf32(unsigned tmem_d, unsigned long long a_desc, unsigned long long b_desc,
-                                            unsigned idesc, unsigned accumulate) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "setp.ne.b32 p, %4, 0;\n"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
-        "}\n" ::"r"(tmem_d), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-__device__ __forceinline__ void cv_mma_commit(unsigned long long *bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(cv_smem_u32(bar))
-                 : "memory");
-}
-__device__ __forceinline__ void cv_tmem_ld32(unsigned taddr, unsigned (&v)[32]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
-        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
-          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
-          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-        : "r"(taddr)
-        : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
-}
-
-// hi = tf32(x), lo = x - hi (exact), both at the offset x has in `raw` (the swizzle permutes 16-byte chunks only)
-__device__ __forceinline__ void cv_split_tile(const unsigned char *raw, unsigned char *hi, unsigned char *lo, int ftid,
-                                              int nthr) {
-    const float4 *r4 = reinterpret_cast<const float4 *>(raw);
-    float4 *h4 = reinterpret_cast<float4 *>(hi);
-    float4 *l4 = reinterpret_cast<float4 *>(lo);
-#pragma unroll 4
-    for (int i = ftid; i < CV_TILE_BYTES / 16; i += nthr) {
-        const float4 x = r4[i];
-        unsigned a, b, c, d;
-        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(a) : "f"(x.x));
-        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(b) : "f"(x.y));
-        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(c) : "f"(x.z));
-        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(d) : "f"(x.w));
-        const float4 hv = make_float4(__uint_as_float(a), __uint_as_float(b), __uint_as_float(c), __uint_as_float(d));
-        h4[i] = hv;
-        l4[i] = make_float4(x.x - hv.x, x.y - hv.y, x.z - hv.z, x.w - hv.w);
-    }
-}
-
 // One warp writes its 32 TMEM lanes x 128 columns of an accumulator to a volume.  Column n is pixel pix0 + n;
 // lane l holds disparity d0 + dl*l + dn*n with (dl, dn) = (+1, -1) for R (lanes = left pixels) and (-1, +1)
 // for L (lanes = right pixels): the 32 lanes of one column are 32 consecutive disparities of one pixel,
@@ -156,7 +63,7 @@ __device__ __forceinline__ void cv_store_quarter(float *__restrict__ vol, unsign
         if (dc + 31 < 0 || dc - 31 >= D) continue;              // (warp uniform)
         if (pix0 + n0 >= W || pix0 + n0 + 31 < 0) continue;
         unsigned v[32];
-        cv_tmem_ld32(taddr + n0, v);
+        tc_tmem_ld32(taddr + n0, v);
         const int dl = dc + DL * lane;                          // this lane's d at column n0
         float *p = vol + ((ptrdiff_t)rowbase + pix0 + n0) * (ptrdiff_t)Dp + dl;
         const bool interior = dc - 31 >= 0 && dc + 31 < D && pix0 + n0 >= 0 && pix0 + n0 + 31 < W &&
@@ -183,19 +90,19 @@ k_cost_volume_tc(const __grid_constant__ CvMaps maps, float *__restrict__ L, flo
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
     if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(cv_smem_u32(&sm.tmem_base)),
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(tc_smem_u32(&sm.tmem_base)),
                      "r"(CV_TMEM_COLS)
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
     }
     if (tid == 32) {
-        cv_mbar_init(&sm.bar_tma_a, 1);
-        cv_mbar_init(&sm.bar_tma_b[0], 1);
-        cv_mbar_init(&sm.bar_tma_b[1], 1);
-        cv_mbar_init(&sm.bar_full[0], 1);
-        cv_mbar_init(&sm.bar_full[1], 1);
-        cv_mbar_init(&sm.bar_empty[0], 256);
-        cv_mbar_init(&sm.bar_empty[1], 256);
+        tc_mbar_init(&sm.bar_tma_a, 1);
+        tc_mbar_init(&sm.bar_tma_b[0], 1);
+        tc_mbar_init(&sm.bar_tma_b[1], 1);
+        tc_mbar_init(&sm.bar_full[0], 1);
+        tc_mbar_init(&sm.bar_full[1], 1);
+        tc_mbar_init(&sm.bar_empty[0], 256);
+        tc_mbar_init(&sm.bar_empty[1], 256);
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
@@ -213,15 +120,15 @@ k_cost_volume_tc(const __grid_constant__ CvMaps maps, float *__restrict__ L, flo
                 const int h = tile / nwt, w0 = (tile - h * nwt) * CV_BM;
                 const int x0c = w0 + CV_BM - CV_BN * nchunks + CV_BN * c;
                 unsigned char *dst = sm.b_hi[g & 1];
-                cv_mbar_expect_tx(&sm.bar_tma_b[g & 1], CV_TILE_BYTES);
-                cv_tma_load_3d(dst, &maps.fr, 0, x0c, h, &sm.bar_tma_b[g & 1]);
-                cv_tma_load_3d(dst + CV_KB_BYTES, &maps.fr, 32, x0c, h, &sm.bar_tma_b[g & 1]);
+                tc_mbar_expect_tx(&sm.bar_tma_b[g & 1], CV_TILE_BYTES);
+                tc_tma_load_3d(dst, &maps.fr, 0, x0c, h, &sm.bar_tma_b[g & 1]);
+                tc_tma_load_3d(dst + CV_KB_BYTES, &maps.fr, 32, x0c, h, &sm.bar_tma_b[g & 1]);
             };
             auto issue_a = [&](int tile) {
                 const int h = tile / nwt, w0 = (tile - h * nwt) * CV_BM;
-                cv_mbar_expect_tx(&sm.bar_tma_a, CV_TILE_BYTES);
-                cv_tma_load_3d(sm.a_raw, &maps.fl, 0, w0, h, &sm.bar_tma_a);
-                cv_tma_load_3d(sm.a_raw + CV_KB_BYTES, &maps.fl, 32, w0, h, &sm.bar_tma_a);
+                tc_mbar_expect_tx(&sm.bar_tma_a, CV_TILE_BYTES);
+                tc_tma_load_3d(sm.a_raw, &maps.fl, 0, w0, h, &sm.bar_tma_a);
+                tc_tma_load_3d(sm.a_raw + CV_KB_BYTES, &maps.fl, 32, w0, h, &sm.bar_tma_a);
             };
             unsigned g = 0;
             if ((int)blockIdx.x < ntiles) {
@@ -232,7 +139,7 @@ k_cost_volume_tc(const __grid_constant__ CvMaps maps, float *__restrict__ L, flo
                 for (int c = 0; c < nchunks; c++, g++) {
                     // chunk g+1 lands in the buffer chunk g-1 used: wait until the MMAs of g-1 are done with it.
                     if (g > 0) {
-                        cv_mbar_wait(&sm.bar_full[(g - 1) & 1], ((g - 1) >> 1) & 1);
+                        tc_mbar_wait_sleep(&sm.bar_full[(g - 1) & 1], ((g - 1) >> 1) & 1);
                         asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
                         // chunk g-1 opened a tile <=> c == 1 (or nchunks == 1): its split has consumed a_raw
                         const bool opened = (nchunks == 1) ? true : (c == 1);
@@ -253,21 +160,21 @@ k_cost_volume_tc(const __grid_constant__ CvMaps maps, float *__restrict__ L, flo
                 if (warp >= 2) {
                     if (c == 0) {
                         // the previous tile's MMAs no longer read a_hi / a_lo; the new tile was prefetched into a_raw
-                        if (g > 0) cv_mbar_wait(&sm.bar_full[(g - 1) & 1], ((g - 1) >> 1) & 1);
-                        cv_mbar_wait(&sm.bar_tma_a, ta & 1);
-                        cv_split_tile(sm.a_raw, sm.a_hi, sm.a_lo, tid - 64, CV_NSPLIT);
+                        if (g > 0) tc_mbar_wait(&sm.bar_full[(g - 1) & 1], ((g - 1) >> 1) & 1);
+                        tc_mbar_wait(&sm.bar_tma_a, ta & 1);
+                        tc_split(sm.a_raw, sm.a_hi, sm.a_lo, CV_TILE_BYTES, tid - 64, CV_NSPLIT);
                     }
-                    cv_mbar_wait(&sm.bar_tma_b[buf], (g >> 1) & 1);
-                    cv_split_tile(sm.b_hi[buf], sm.b_hi[buf], sm.b_lo[buf], tid - 64, CV_NSPLIT);
+                    tc_mbar_wait(&sm.bar_tma_b[buf], (g >> 1) & 1);
+                    tc_split(sm.b_hi[buf], sm.b_hi[buf], sm.b_lo[buf], CV_TILE_BYTES, tid - 64, CV_NSPLIT);
                     asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");   // operand accesses -> async proxy
                 }
-                cv_named_barrier(1, 32 + CV_NSPLIT);
+                tc_named_barrier(1, 32 + CV_NSPLIT);
                 if (tid == 0) {
-                    if (g >= 2) cv_mbar_wait(&sm.bar_empty[buf], ((g >> 1) - 1) & 1);   // accumulators drained by the epilogue
+                    if (g >= 2) tc_mbar_wait(&sm.bar_empty[buf], ((g >> 1) - 1) & 1);   // accumulators drained by the epilogue
                     asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
                     const unsigned d_s = tmem_base + buf * (2 * CV_BN), d_t = d_s + CV_BN;
-                    const unsigned long long ah = cv_smem_desc(cv_smem_u32(sm.a_hi)), al = cv_smem_desc(cv_smem_u32(sm.a_lo));
-                    const unsigned long long bh = cv_smem_desc(cv_smem_u32(sm.b_hi[buf])), bl = cv_smem_desc(cv_smem_u32(sm.b_lo[buf]));
+                    const unsigned long long ah = tc_smem_desc(tc_smem_u32(sm.a_hi)), al = tc_smem_desc(tc_smem_u32(sm.a_lo));
+                    const unsigned long long bh = tc_smem_desc(tc_smem_u32(sm.b_hi[buf])), bl = tc_smem_desc(tc_smem_u32(sm.b_lo[buf]));
                     unsigned acc = 0;
 #pragma unroll
                     for (int kb = 0; kb < 2; kb++)
@@ -275,15 +182,15 @@ k_cost_volume_tc(const __grid_constant__ CvMaps maps, float *__restrict__ L, flo
                         for (int ks = 0; ks < 4; ks++) {
                             const unsigned long long off = (unsigned long long)((kb * CV_KB_BYTES + ks * 32) >> 4);
                             // S = -FL.FR^T (lanes = left pixels) and S^T (lanes = right pixels), each hi.hi + hi.lo + lo.hi
-                            cv_mma_tf32(d_s, ah + off, bh + off, idesc, acc);
-                            cv_mma_tf32(d_t, bh + off, ah + off, idesc, acc);
+                            tc_mma_tf32(d_s, ah + off, bh + off, idesc, acc);
+                            tc_mma_tf32(d_t, bh + off, ah + off, idesc, acc);
                             acc = 1;
-                            cv_mma_tf32(d_s, ah + off, bl + off, idesc, 1);
-                            cv_mma_tf32(d_t, bh + off, al + off, idesc, 1);
-                            cv_mma_tf32(d_s, al + off, bh + off, idesc, 1);
-                            cv_mma_tf32(d_t, bl + off, ah + off, idesc, 1);
+                            tc_mma_tf32(d_s, ah + off, bl + off, idesc, 1);
+                            tc_mma_tf32(d_t, bh + off, al + off, idesc, 1);
+                            tc_mma_tf32(d_s, al + off, bh + off, idesc, 1);
+                            tc_mma_tf32(d_t, bl + off, ah + off, idesc, 1);
                         }
-                    cv_mma_commit(&sm.bar_full[buf]);
+                    tc_mma_commit(&sm.bar_full[buf]);
                 }
             }
         }
@@ -299,7 +206,7 @@ k_cost_volume_tc(const __grid_constant__ CvMaps maps, float *__restrict__ L, flo
             for (int c = 0; c < nchunks; c++, g++) {
                 const unsigned buf = g & 1;
                 const int x0c = x_lo + CV_BN * c;
-                cv_mbar_wait(&sm.bar_full[buf], (g >> 1) & 1);
+                tc_mbar_wait(&sm.bar_full[buf], (g >> 1) & 1);
                 asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
                 const unsigned t_s = tmem_base + ((unsigned)(32 * q) << 16) + buf * (2 * CV_BN), t_t = t_s + CV_BN;
                 if (!does_l) {
@@ -310,7 +217,7 @@ k_cost_volume_tc(const __grid_constant__ CvMaps maps, float *__restrict__ L, flo
                     cv_store_quarter<-1>(L, t_t, rowbase, w0, w0 - x0c - 32 * q, true, W, D, Dp);
                 }
                 asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
-                cv_mbar_arrive(&sm.bar_empty[buf]);
+                tc_mbar_arrive(&sm.bar_empty[buf]);
             }
         }
     }
@@ -361,35 +268,6 @@ __global__ void k_cost_fill(float *__restrict__ L, float *__restrict__ R, int H,
     }
 }
 
-typedef CUresult (*CvEncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
-                                    const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
-                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static int cv_feature_map(CUtensorMap &map, const float *f, int H, int W) {
-    static CvEncodeTiledFn enc = nullptr;
-    if (!enc) {
-        void *p = nullptr;
-        cudaDriverEntryPointQueryResult qres;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess ||
-            qres != cudaDriverEntryPointSuccess) {
-            set_error("cost_volume: cuTensorMapEncodeTiled is not available from this driver");
-            return MCCNN_ERR_CUDA;
-        }
-        enc = (CvEncodeTiledFn)p;
-    }
-    const cuuint64_t gdim[3] = {CV_C, (cuuint64_t)W, (cuuint64_t)H};
-    const cuuint64_t gstr[2] = {CV_C * 4, (cuuint64_t)W * CV_C * 4};
-    const cuuint32_t box[3] = {32, CV_BM, 1};
-    const cuuint32_t estr[3] = {1, 1, 1};
-    CUresult r = enc(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void *)f, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) {
-        set_error("cost_volume: cuTensorMapEncodeTiled failed (%d)", (int)r);
-        return MCCNN_ERR_CUDA;
-    }
-    return MCCNN_OK;
-}
-
 }  // namespace mccnn
 
 using namespace mccnn;
@@ -405,9 +283,9 @@ int mccnn_cost_volume(const float *fl, const float *fr, float *L, float *R, int 
     cudaStream_t s = (cudaStream_t)stream;
     const int Dp = dpitch(D);
     CvMaps maps;
-    int rc = cv_feature_map(maps.fl, fl, H, W);
+    int rc = tc_encode_map_3d(maps.fl, fl, CV_C, W, H, 32, CV_BM, true, "cost_volume");
     if (rc) return rc;
-    rc = cv_feature_map(maps.fr, fr, H, W);
+    rc = tc_encode_map_3d(maps.fr, fr, CV_C, W, H, 32, CV_BM, true, "cost_volume");
     if (rc) return rc;
     static int num_sms = 0;
     static bool smem_set = false;

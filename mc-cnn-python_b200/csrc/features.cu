@@ -3,12 +3,10 @@
 // cross-correlations with 64 maps (NHWC activations, HWIO weights, stride 1), bias, ReLU after all
 // but the last (model.py:51-60), and x * rsqrt(max(sum_c x^2, 1e-12)) over channels (model.py:64).
 //
-// Direct-convolution fp32 kernels (the 1e-4 cost-volume tolerance rules out plain TF32/BF16
-// tensor-core math).  k_conv1 is bandwidth bound (1 input channel).  k_conv64 is an
-// implicit GEMM with M = 128 output pixels (8 x 16 tile), N = 64, K = 576 walked in chunks of 8
-// input channels staged in shared memory; each thread owns 8 pixels x 8 channels and reuses the 10
-// activations of a patch row across the three horizontal taps (9 shared loads per 192 FMAs).
-#include "common.cuh"
+// k_conv1 (1 -> 64) is a bandwidth-bound float32 SIMT kernel.  Layers 2..n (64 -> 64, 99.8 % of the
+// flops) run on the tensor cores as implicit GEMMs, k_conv64_tc below; plain TF32/BF16 would break the
+// 1e-4 cost-volume tolerance, so operands are split into tf32 hi + lo and three products are accumulated.
+#include "tc_common.cuh"
 
 namespace mccnn {
 
@@ -45,109 +43,244 @@ __global__ void __launch_bounds__(256) k_conv1(const float *__restrict__ img, co
     reinterpret_cast<float4 *>(out)[px * 16 + (oc >> 2)] = acc;
 }
 
-// Layers 2..n: 64 -> 64.
-constexpr int CT_H = 8, CT_W = 16;             // output tile
-constexpr int ICC = 8;                         // input channels per shared-memory chunk
-constexpr int PR = CT_H + 2, PC = CT_W + 2;    // patch rows / cols
-constexpr int PCP = 20;                        // padded patch row pitch (floats)
+// ------------------------------------------------------------------------------------------
+// Layers 2..n on the tensor cores.  A 3x3 VALID convolution with 64 maps in and out is the implicit GEMM
+// out[p][oc] = sum_{tap, ic} in[p + tap][ic] * w[tap][ic][oc]  (M = pixels, N = 64, K = 9 * 64), dense enough
+// for tcgen05; float32 accuracy is kept with the three-way TF32 split (hi.hi + hi.lo + lo.hi, float32
+// accumulation in TMEM), as in the cost-volume kernel.
+//
+// k_conv64_tc: persistent, one CTA per SM.  A tile is 4 output rows x 126 output pixels; its four
+// accumulators (128 lanes = pixels, 64 columns = output maps each) live in TMEM, double buffered across
+// tiles so that the epilogue of a tile overlaps the next tile's MMAs.  The input channels are processed in
+// two blocks of 32 (one 128-byte swizzled row per pixel): for a channel block the weights of all nine taps,
+// pre-split into hi / lo (k_conv_prep_weights), are resident in shared memory (144 KB) and the six input
+// rows the tile touches stream through a double-buffered 128-pixel row buffer that is split in place.  The
+// three horizontal taps are the same rows read through descriptors whose start address is shifted by
+// 0 / 1 / 2 pixels (the 128B swizzle is a function of the absolute shared-memory address, so a start that
+// is not 1024-byte aligned needs no base offset -- checked on the device), which is why a tile yields 126
+// pixels, not 128.  Consecutive tiles visit the channel blocks in opposite order, so the weights are
+// reloaded once per tile, not twice.
+//   warp 0: MMA issue (one lane); warp 1: TMA producer (one lane); warps 2-7: operand split;
+//   warps 8-15: epilogue -- bias, ReLU or (last layer) channel L2 normalisation, 256-bit stores.
+// ------------------------------------------------------------------------------------------
+constexpr int CT_ROWS = 4;                      // output rows per tile
+constexpr int CT_PIX = 126;                     // output pixels per tile row (128 loaded - 2 for the horizontal taps)
+constexpr int CT_ROW_BYTES = 128 * 128;         // one input row block: 128 pixels x 32 channels, 128B-swizzled
+constexpr int CT_WBLK_BYTES = 64 * 128;         // one weight block: 64 output maps x 32 input channels
+constexpr int CT_W_BYTES = 9 * 2 * CT_WBLK_BYTES;   // nine taps, hi and lo: 144 KB
+constexpr int CT_THREADS = 512;
+constexpr int CT_NSPLIT = 192;
+
+struct __align__(1024) CtcSmem {
+    unsigned char w[9][2][CT_WBLK_BYTES];        // [tap][hi, lo]
+    unsigned char a_hi[2][CT_ROW_BYTES], a_lo[2][CT_ROW_BYTES];
+    unsigned long long bar_w, bar_row[2], bar_rowdone[2], bar_full[2], bar_empty[2];
+    unsigned tmem_base;
+};
+
+struct CtcMaps { CUtensorMap in, whi, wlo; };   // in: [IH][IW][64], box {32, 128, 1}; w: [9][64 oc][64 ic], box {32, 64, 1}
+
+// HWIO [3][3][ic][oc] -> [tap][oc][ic], split into hi = tf32(w) and lo = w - hi
+__global__ void k_conv_prep_weights(const float *__restrict__ w, float *__restrict__ whi, float *__restrict__ wlo) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;        // index into [tap][oc][ic]
+    if (i >= 9 * F * F) return;
+    const int ic = i % F, oc = (i / F) % F, tap = i / (F * F);
+    const float x = w[((size_t)tap * F + ic) * F + oc];
+    const float h = __uint_as_float(tc_tf32(x));
+    whi[i] = h;
+    wlo[i] = x - h;
+}
 
 template <bool LAST>
-__global__ void __launch_bounds__(128) k_conv64(const float *__restrict__ in, const float *__restrict__ wgt,
-                                                const float *__restrict__ bias, float *__restrict__ out, int IH, int IW,
-                                                int OH, int OW) {
-    __shared__ __align__(16) float patch[ICC][PR][PCP];
-    __shared__ __align__(16) float wsm[9][ICC][F];
-    const int tid = threadIdx.x;
-    const int ocg = tid & 7, pxg = tid >> 3;
-    const int row = pxg >> 1, c0 = (pxg & 1) * 8;
-    const int y0 = blockIdx.y * CT_H, x0 = blockIdx.x * CT_W;
+__global__ void __launch_bounds__(CT_THREADS, 1)
+k_conv64_tc(const __grid_constant__ CtcMaps maps, const float *__restrict__ bias, float *__restrict__ out, int OH, int OW,
+            int ntx, int ntiles) {
+    extern __shared__ __align__(1024) unsigned char ctc_raw[];
+    CtcSmem &sm = *reinterpret_cast<CtcSmem *>(ctc_raw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
-    float acc[8][8];
-#pragma unroll
-    for (int p = 0; p < 8; p++)
-#pragma unroll
-        for (int o = 0; o < 8; o++) acc[p][o] = 0.f;
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(tc_smem_u32(&sm.tmem_base)),
+                     "r"(512)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+    }
+    if (tid == 32) {
+        tc_mbar_init(&sm.bar_w, 1);
+        for (int i = 0; i < 2; i++) {
+            tc_mbar_init(&sm.bar_row[i], 1);
+            tc_mbar_init(&sm.bar_rowdone[i], 1);
+            tc_mbar_init(&sm.bar_full[i], 1);
+            tc_mbar_init(&sm.bar_empty[i], 256);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+    const unsigned tmem_base = sm.tmem_base;
+    // instruction descriptor: D = F32, A = B = TF32, both K-major, N = 64, M = 128
+    const unsigned idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((unsigned)(F >> 3) << 17) | ((unsigned)(128 >> 4) << 24);
+    constexpr int NROW = CT_ROWS + 2;           // input rows per tile
 
-    for (int ic0 = 0; ic0 < F; ic0 += ICC) {
-        __syncthreads();
-        // activations: PR x PC pixels x 8 channels (two float4 per pixel), transposed to [ic][row][col]
-        for (int i = tid; i < PR * PC * 2; i += 128) {
-            int half = i & 1, pix = i >> 1;
-            int r = pix / PC, c = pix % PC;
-            int iy = y0 + r, ix = x0 + c;
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (iy < IH && ix < IW)
-                v = *reinterpret_cast<const float4 *>(in + ((size_t)iy * IW + ix) * F + ic0 + half * 4);
-            patch[half * 4 + 0][r][c] = v.x;
-            patch[half * 4 + 1][r][c] = v.y;
-            patch[half * 4 + 2][r][c] = v.z;
-            patch[half * 4 + 3][r][c] = v.w;
-        }
-        // weights: [tap][ic0..ic0+7][64]
-        for (int i = tid; i < 9 * ICC * (F / 4); i += 128) {
-            int tap = i / (ICC * 16), rem = i % (ICC * 16);
-            int ic = rem >> 4, o4 = rem & 15;
-            reinterpret_cast<float4 *>(&wsm[tap][ic][0])[o4] =
-                *reinterpret_cast<const float4 *>(wgt + ((size_t)(tap * F + ic0 + ic)) * F + o4 * 4);
-        }
-        __syncthreads();
-#pragma unroll 1
-        for (int ic = 0; ic < ICC; ic++) {
-#pragma unroll
-            for (int ky = 0; ky < 3; ky++) {
-                float a[10];
-                const float *pr = &patch[ic][row + ky][c0];
-                float4 a0 = *reinterpret_cast<const float4 *>(pr);
-                float4 a1 = *reinterpret_cast<const float4 *>(pr + 4);
-                float2 a2 = *reinterpret_cast<const float2 *>(pr + 8);
-                a[0] = a0.x; a[1] = a0.y; a[2] = a0.z; a[3] = a0.w;
-                a[4] = a1.x; a[5] = a1.y; a[6] = a1.z; a[7] = a1.w;
-                a[8] = a2.x; a[9] = a2.y;
-#pragma unroll
-                for (int kx = 0; kx < 3; kx++) {
-                    const float4 *wp = reinterpret_cast<const float4 *>(&wsm[ky * 3 + kx][ic][ocg * 8]);
-                    float4 w0 = wp[0], w1 = wp[1];
-                    float w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
-#pragma unroll
-                    for (int p = 0; p < 8; p++)
-#pragma unroll
-                        for (int o = 0; o < 8; o++) acc[p][o] = fmaf(a[p + kx], w[o], acc[p][o]);
+    // A tile visits the channel blocks in the order (t & 1), (t & 1) ^ 1, so the block the previous tile ended with
+    // is still resident.  Row steps are numbered globally: rr = (tile ordinal * 2 + block ordinal) * NROW + r.
+    if (warp == 1) {
+        // ================= TMA producer (one lane) =================
+        if (lane == 0) {
+            unsigned rr = 0, wloads = 0;
+            int resident = -1;
+            unsigned tt = 0;
+            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, tt++) {
+                const int ty = tile / ntx, y0 = ty * CT_ROWS, x0 = (tile - ty * ntx) * CT_PIX;
+                for (int bi = 0; bi < 2; bi++) {
+                    const int kb = (tt & 1) ^ bi;
+                    if (kb != resident) {
+                        // every MMA issued so far reads the resident weights: wait for the last row step
+                        if (rr > 0) {
+                            tc_mbar_wait_sleep(&sm.bar_rowdone[(rr - 1) & 1], ((rr - 1) >> 1) & 1);
+                            asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+                        }
+                        tc_mbar_expect_tx(&sm.bar_w, CT_W_BYTES);
+                        for (int tap = 0; tap < 9; tap++) {
+                            tc_tma_load_3d(sm.w[tap][0], &maps.whi, kb * 32, 0, tap, &sm.bar_w);
+                            tc_tma_load_3d(sm.w[tap][1], &maps.wlo, kb * 32, 0, tap, &sm.bar_w);
+                        }
+                        resident = kb;
+                        wloads++;
+                    }
+                    for (int r = 0; r < NROW; r++, rr++) {
+                        // the row buffer was last used by step rr - 2
+                        if (rr >= 2) {
+                            tc_mbar_wait_sleep(&sm.bar_rowdone[rr & 1], ((rr - 2) >> 1) & 1);
+                            asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+                        }
+                        tc_mbar_expect_tx(&sm.bar_row[rr & 1], CT_ROW_BYTES);
+                        tc_tma_load_3d(sm.a_hi[rr & 1], &maps.in, kb * 32, x0, y0 + r, &sm.bar_row[rr & 1]);
+                    }
                 }
             }
         }
-    }
-
-    // epilogue: bias, then ReLU (model.py:120-123) or, on the last layer, channel L2-normalisation
-    float b[8];
+    } else if (warp < 8) {
+        // ================= operand split (warps 2-7) and MMA issue (warp 0, lane 0) =================
+        unsigned rr = 0, wloads = 0, tt = 0;
+        int resident = -1;
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, tt++) {
+            const unsigned abuf = tt & 1;
+            for (int bi = 0; bi < 2; bi++) {
+                const int kb = (tt & 1) ^ bi;
+                bool new_weights = false;
+                if (kb != resident) { new_weights = true; resident = kb; }
+                for (int r = 0; r < NROW; r++, rr++) {
+                    const unsigned rb = rr & 1;
+                    if (warp >= 2) {
+                        tc_mbar_wait(&sm.bar_row[rb], (rr >> 1) & 1);
+                        tc_split(sm.a_hi[rb], sm.a_hi[rb], sm.a_lo[rb], CT_ROW_BYTES, tid - 64, CT_NSPLIT);
+                        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+                    }
+                    tc_named_barrier(1, 32 + CT_NSPLIT);
+                    if (tid == 0) {
+                        if (new_weights && r == 0) { tc_mbar_wait(&sm.bar_w, wloads & 1); }
+                        if (bi == 0 && r == 0 && tt >= 2) tc_mbar_wait(&sm.bar_empty[abuf], ((tt >> 1) - 1) & 1);
+                        asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+                        const unsigned long long ah = tc_smem_desc(tc_smem_u32(sm.a_hi[rb])), al = tc_smem_desc(tc_smem_u32(sm.a_lo[rb]));
 #pragma unroll
-    for (int o = 0; o < 8; o++) b[o] = bias[ocg * 8 + o];
-    const int y = y0 + row;
+                        for (int j = 0; j < CT_ROWS; j++) {
+                            const int ky = r - j;
+                            if (ky < 0 || ky > 2) continue;
+                            const unsigned d_tmem = tmem_base + abuf * (CT_ROWS * F) + j * F;
 #pragma unroll
-    for (int p = 0; p < 8; p++) {
-        float v[8];
+                            for (int kx = 0; kx < 3; kx++) {
+                                const int tap = ky * 3 + kx;
+                                const unsigned long long wh = tc_smem_desc(tc_smem_u32(sm.w[tap][0])), wl = tc_smem_desc(tc_smem_u32(sm.w[tap][1]));
 #pragma unroll
-        for (int o = 0; o < 8; o++) v[o] = acc[p][o] + b[o];
-        if (LAST) {
-            float ss = 0.f;
-#pragma unroll
-            for (int o = 0; o < 8; o++) ss = fmaf(v[o], v[o], ss);
-            ss += __shfl_xor_sync(0xffffffffu, ss, 1);
-            ss += __shfl_xor_sync(0xffffffffu, ss, 2);
-            ss += __shfl_xor_sync(0xffffffffu, ss, 4);
-            const float inv = 1.0f / sqrtf(fmaxf(ss, 1e-12f));          // model.py:64
-#pragma unroll
-            for (int o = 0; o < 8; o++) v[o] *= inv;
-        } else {
-#pragma unroll
-            for (int o = 0; o < 8; o++) v[o] = fmaxf(v[o], 0.f);
+                                for (int ks = 0; ks < 4; ks++) {
+                                    const unsigned long long aoff = (unsigned long long)((kx * 128 + ks * 32) >> 4);
+                                    const unsigned long long woff = (unsigned long long)((ks * 32) >> 4);
+                                    // first MMA into accumulator j of this tile: first block, tap (0,0), first K step
+                                    const unsigned acc = (bi == 0 && ky == 0 && kx == 0 && ks == 0) ? 0u : 1u;
+                                    tc_mma_tf32(d_tmem, ah + aoff, wh + woff, idesc, acc);
+                                    tc_mma_tf32(d_tmem, ah + aoff, wl + woff, idesc, 1);
+                                    tc_mma_tf32(d_tmem, al + aoff, wh + woff, idesc, 1);
+                                }
+                            }
+                        }
+                        tc_mma_commit(&sm.bar_rowdone[rb]);
+                        if (bi == 1 && r == NROW - 1) tc_mma_commit(&sm.bar_full[abuf]);
+                    }
+                }
+                if (new_weights) wloads++;
+            }
         }
-        const int x = x0 + c0 + p;
-        if (y < OH && x < OW) {
-            float4 *dst = reinterpret_cast<float4 *>(out + ((size_t)y * OW + x) * F + ocg * 8);
-            dst[0] = make_float4(v[0], v[1], v[2], v[3]);
-            dst[1] = make_float4(v[4], v[5], v[6], v[7]);
+    } else {
+        // ================= epilogue (warps 8-15): two warps per TMEM lane quarter, two output rows each =================
+        const int q = warp & 3, half = (warp - 8) >> 2;
+        const int m = 32 * q + lane;
+        const float4 *b4 = reinterpret_cast<const float4 *>(bias);
+        unsigned tt = 0;
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, tt++) {
+            const unsigned abuf = tt & 1;
+            const int ty = tile / ntx, y0 = ty * CT_ROWS, x0 = (tile - ty * ntx) * CT_PIX;
+            tc_mbar_wait(&sm.bar_full[abuf], (tt >> 1) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+#pragma unroll 1
+            for (int jj = 0; jj < CT_ROWS / 2; jj++) {
+                const int j = half * (CT_ROWS / 2) + jj;
+                const int y = y0 + j, x = x0 + m;
+                unsigned v0[32], v1[32];
+                const unsigned taddr = tmem_base + ((unsigned)(32 * q) << 16) + abuf * (CT_ROWS * F) + j * F;
+                tc_tmem_ld32(taddr, v0);
+                tc_tmem_ld32(taddr + 32, v1);
+                float ss = 0.f;
+#pragma unroll
+                for (int o = 0; o < 32; o += 4) {
+                    const float4 ba = __ldg(b4 + (o >> 2)), bb = __ldg(b4 + 8 + (o >> 2));
+                    float t;
+                    t = __uint_as_float(v0[o]) + ba.x;     v0[o] = __float_as_uint(t);     ss = fmaf(t, t, ss);
+                    t = __uint_as_float(v0[o + 1]) + ba.y; v0[o + 1] = __float_as_uint(t); ss = fmaf(t, t, ss);
+                    t = __uint_as_float(v0[o + 2]) + ba.z; v0[o + 2] = __float_as_uint(t); ss = fmaf(t, t, ss);
+                    t = __uint_as_float(v0[o + 3]) + ba.w; v0[o + 3] = __float_as_uint(t); ss = fmaf(t, t, ss);
+                    t = __uint_as_float(v1[o]) + bb.x;     v1[o] = __float_as_uint(t);     ss = fmaf(t, t, ss);
+                    t = __uint_as_float(v1[o + 1]) + bb.y; v1[o + 1] = __float_as_uint(t); ss = fmaf(t, t, ss);
+                    t = __uint_as_float(v1[o + 2]) + bb.z; v1[o + 2] = __float_as_uint(t); ss = fmaf(t, t, ss);
+                    t = __uint_as_float(v1[o + 3]) + bb.w; v1[o + 3] = __float_as_uint(t); ss = fmaf(t, t, ss);
+                }
+                const float inv = LAST ? 1.0f / sqrtf(fmaxf(ss, 1e-12f)) : 1.0f;   // model.py:64
+                if (y < OH && m < CT_PIX && x < OW) {
+                    float *dst = out + ((size_t)y * OW + x) * F;
+#pragma unroll
+                    for (int o = 0; o < 32; o += 8) {
+                        float e[8];
+#pragma unroll
+                        for (int k = 0; k < 8; k++) {
+                            const float t = __uint_as_float(v0[o + k]);
+                            e[k] = LAST ? t * inv : fmaxf(t, 0.f);                  // model.py:120-123
+                        }
+                        asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(dst + o), "f"(e[0]), "f"(e[1]),
+                                     "f"(e[2]), "f"(e[3]), "f"(e[4]), "f"(e[5]), "f"(e[6]), "f"(e[7])
+                                     : "memory");
+                    }
+#pragma unroll
+                    for (int o = 0; o < 32; o += 8) {
+                        float e[8];
+#pragma unroll
+                        for (int k = 0; k < 8; k++) {
+                            const float t = __uint_as_float(v1[o + k]);
+                            e[k] = LAST ? t * inv : fmaxf(t, 0.f);
+                        }
+                        asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(dst + 32 + o), "f"(e[0]), "f"(e[1]),
+                                     "f"(e[2]), "f"(e[3]), "f"(e[4]), "f"(e[5]), "f"(e[6]), "f"(e[7])
+                                     : "memory");
+                    }
+                }
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+            tc_mbar_arrive(&sm.bar_empty[abuf]);
         }
     }
+    asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"(512) : "memory");
 }
 
 // Single-layer network (num_layers == 1): normalise the conv1 output in place.
@@ -172,10 +305,13 @@ using namespace mccnn;
 
 extern "C" {
 
+static size_t conv_weights_floats(int num_layers) { return (size_t)(num_layers > 1 ? num_layers - 1 : 0) * 2 * 9 * F * F; }
+
 size_t mccnn_features_scratch_bytes(int H, int W, int pad, int num_layers) {
     if (H < 1 || W < 1 || num_layers < 1 || pad < 0 || H + 2 * pad < 3 || W + 2 * pad < 3) return 0;
     size_t oh = (size_t)H + 2 * pad - 2, ow = (size_t)W + 2 * pad - 2;
-    return 2 * oh * ow * F * sizeof(float);
+    // two ping-pong activation maps + the pre-split weights of layers 2..n
+    return (2 * oh * ow * F + conv_weights_floats(num_layers)) * sizeof(float);
 }
 
 int mccnn_features(const float *img, int H, int W, int pad, int num_layers, const float *const *weights_host,
@@ -186,11 +322,13 @@ int mccnn_features(const float *img, int H, int W, int pad, int num_layers, cons
     MCCNN_REQUIRE(H + 2 * pad - 2 * num_layers >= 1 && W + 2 * pad - 2 * num_layers >= 1,
                   "features: image %dx%d (pad %d) too small for %d VALID 3x3 layers", H, W, pad, num_layers);
     MCCNN_REQUIRE(num_layers == 1 || scratch, "features: scratch required");
+    MCCNN_REQUIRE(((uintptr_t)out & 31) == 0 && ((uintptr_t)scratch & 31) == 0, "features: out and scratch must be 32-byte aligned");
     cudaStream_t s = (cudaStream_t)stream;
     int oh = H + 2 * pad - 2, ow = W + 2 * pad - 2;
     float *buf[2];
     buf[0] = (float *)scratch;
     buf[1] = buf[0] ? buf[0] + (size_t)oh * ow * F : nullptr;
+    float *wsplit = buf[0] ? buf[1] + (size_t)oh * ow * F : nullptr;
     float *dst = (num_layers == 1) ? out : buf[0];
     {
         long long threads = (long long)oh * ow * 16;
@@ -204,16 +342,40 @@ int mccnn_features(const float *img, int H, int W, int pad, int num_layers, cons
         MCCNN_LAUNCHED("l2norm64");
         return MCCNN_OK;
     }
+    static int num_sms = 0;
+    static bool smem_set = false;
+    if (num_sms == 0) {
+        int dev = 0;
+        MCCNN_CUDA(cudaGetDevice(&dev));
+        MCCNN_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+    }
+    if (!smem_set) {
+        MCCNN_CUDA(cudaFuncSetAttribute(k_conv64_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CtcSmem)));
+        MCCNN_CUDA(cudaFuncSetAttribute(k_conv64_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CtcSmem)));
+        smem_set = true;
+    }
     const float *src = dst;
     int ih = oh, iw = ow;
     for (int l = 1; l < num_layers; l++) {
         oh = ih - 2; ow = iw - 2;
         const bool last = (l == num_layers - 1);
         float *d = last ? out : buf[l & 1];
-        dim3 grid(cdiv(ow, CT_W), cdiv(oh, CT_H));
-        if (last) k_conv64<true><<<grid, 128, 0, s>>>(src, weights_host[l], biases_host[l], d, ih, iw, oh, ow);
-        else k_conv64<false><<<grid, 128, 0, s>>>(src, weights_host[l], biases_host[l], d, ih, iw, oh, ow);
-        MCCNN_LAUNCHED("conv64");
+        float *whi = wsplit + (size_t)(l - 1) * 2 * 9 * F * F, *wlo = whi + 9 * F * F;
+        k_conv_prep_weights<<<cdiv(9 * F * F, 256), 256, 0, s>>>(weights_host[l], whi, wlo);
+        MCCNN_LAUNCHED("conv_prep_weights");
+        CtcMaps maps;
+        int rc = tc_encode_map_3d(maps.in, src, F, iw, ih, 32, 128, true, "features");
+        if (rc) return rc;
+        rc = tc_encode_map_3d(maps.whi, whi, F, F, 9, 32, F, true, "features");
+        if (rc) return rc;
+        rc = tc_encode_map_3d(maps.wlo, wlo, F, F, 9, 32, F, true, "features");
+        if (rc) return rc;
+        const int ntx = cdiv(ow, CT_PIX), nty = cdiv(oh, CT_ROWS);
+        const int ntiles = ntx * nty;
+        const int grid = ntiles < num_sms ? ntiles : num_sms;
+        if (last) k_conv64_tc<true><<<grid, CT_THREADS, sizeof(CtcSmem), s>>>(maps, biases_host[l], d, oh, ow, ntx, ntiles);
+        else k_conv64_tc<false><<<grid, CT_THREADS, sizeof(CtcSmem), s>>>(maps, biases_host[l], d, oh, ow, ntx, ntiles);
+        MCCNN_LAUNCHED("conv64_tc");
         src = d; ih = oh; iw = ow;
     }
     return MCCNN_OK;
