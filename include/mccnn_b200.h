@@ -80,12 +80,14 @@ int mccnn_cross_region_list(const uint8_t *arms, int32_t *region, int H, int W,
  * `iters` rounds of region mean; in is left untouched, out receives the result, scratch is one
  * more HWD volume.
  * mode MCCNN_CBCA_SEPARABLE: row sums re-used down each column (<= 54 additions per cell); equals the
- *      reference up to float32 re-association of the sum (~1e-7 relative).  Needs the
- *      distance_threshold the arms were built with to be <= 14 (match.py:34 default) and a
- *      workspace of mccnn_cbca_workspace_bytes(H, W) bytes (per-tile halo table, rebuilt per call).
+ *      reference up to float32 re-association of the sum (~1e-7 relative).  Two streaming passes per
+ *      round (rows into `scratch`, columns into `out`): `scratch` is needed for any iters >= 1.
+ * mode MCCNN_CBCA_SEPARABLE_TILED: the same sums in one fused kernel per round (TMA-staged shared-memory
+ *      tiles).  Needs distance_threshold <= 14 (match.py:34 default) and a workspace of
+ *      mccnn_cbca_workspace_bytes(H, W) bytes (per-tile halo table and schedule, rebuilt per call).
  * mode MCCNN_CBCA_EXACT: one float32 running sum over the whole region in the reference's enumeration
  *      order (pf:149-163), bit-identical to the reference (<= 729 additions per cell). */
-enum mccnn_cbca_mode { MCCNN_CBCA_SEPARABLE = 0, MCCNN_CBCA_EXACT = 1 };
+enum mccnn_cbca_mode { MCCNN_CBCA_SEPARABLE = 0, MCCNN_CBCA_EXACT = 1, MCCNN_CBCA_SEPARABLE_TILED = 2 };
 size_t mccnn_cbca_workspace_bytes(int H, int W);
 int mccnn_cbca(const float *in, float *out, float *scratch, const uint8_t *arms,
                const int32_t *count, int D, int H, int W, int iters, int distance_threshold, int mode,

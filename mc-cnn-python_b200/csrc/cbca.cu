@@ -9,6 +9,7 @@
 // 16 B granule of the neighbour pixel's disparity row (fully coalesced for any region shape).
 #include "common.cuh"
 #include "cbca_tile.cuh"
+#include "cbca_stream.cuh"
 
 namespace mccnn {
 
@@ -193,21 +194,38 @@ size_t mccnn_cbca_workspace_bytes(int H, int W) {
 
 int mccnn_cbca(const float *in, float *out, float *scratch, const uint8_t *arms, const int32_t *count, int D, int H,
                int W, int iters, int dist, int mode, void *workspace, void *stream) {
-    MCCNN_REQUIRE(mode == MCCNN_CBCA_SEPARABLE || mode == MCCNN_CBCA_EXACT, "cbca: unknown mode %d", mode);
+    MCCNN_REQUIRE(mode == MCCNN_CBCA_SEPARABLE || mode == MCCNN_CBCA_EXACT || mode == MCCNN_CBCA_SEPARABLE_TILED,
+                  "cbca: unknown mode %d", mode);
     MCCNN_REQUIRE(dist >= 1 && dist <= 255, "cbca: distance_threshold %d outside [1, 255]", dist);
-    MCCNN_REQUIRE(mode == MCCNN_CBCA_EXACT || dist <= CT_MAXARM + 1,
+    MCCNN_REQUIRE(mode != MCCNN_CBCA_SEPARABLE_TILED || dist <= CT_MAXARM + 1,
                   "cbca: separable mode supports distance_threshold <= 14 (got %d); use MCCNN_CBCA_EXACT", dist);
     MCCNN_REQUIRE(in && out && arms && count && D >= 1 && H >= 1 && W >= 1 && iters >= 0, "cbca: bad arguments");
     MCCNN_REQUIRE(H <= 65535 && W <= 65535, "cbca: image too large");
     MCCNN_REQUIRE(in != out, "cbca: in and out must differ (the reference leaves its input untouched, pf:119)");
-    MCCNN_REQUIRE(iters < 2 || (scratch && scratch != in && scratch != out), "cbca: scratch volume required for iters >= 2");
-    MCCNN_REQUIRE(mode == MCCNN_CBCA_EXACT || iters <= CBCA_MAX_ROUNDS, "cbca: at most %d rounds per call", CBCA_MAX_ROUNDS);
-    MCCNN_REQUIRE(mode == MCCNN_CBCA_EXACT || iters == 0 || workspace,
+    MCCNN_REQUIRE(iters < (mode == MCCNN_CBCA_SEPARABLE ? 1 : 2) || (scratch && scratch != in && scratch != out),
+                  "cbca: scratch volume required (separable: any round; other modes: iters >= 2)");
+    MCCNN_REQUIRE(mode != MCCNN_CBCA_SEPARABLE_TILED || iters <= CBCA_MAX_ROUNDS, "cbca: at most %d rounds per call", CBCA_MAX_ROUNDS);
+    MCCNN_REQUIRE(mode != MCCNN_CBCA_SEPARABLE_TILED || iters == 0 || workspace,
                   "cbca: separable mode needs a workspace of mccnn_cbca_workspace_bytes(H, W) bytes");
     cudaStream_t s = (cudaStream_t)stream;
     const int Dp = dpitch(D), G = Dp / 4;
     if (iters == 0) {
         MCCNN_CUDA(cudaMemcpyAsync(out, in, (size_t)H * W * Dp * sizeof(float), cudaMemcpyDeviceToDevice, s));
+        return MCCNN_OK;
+    }
+    if (mode == MCCNN_CBCA_SEPARABLE) {
+        // every round: row sums src -> scratch, column sums scratch -> out; the next round reads out
+        dim3 sgrid(cdiv(W, CS_PW), cdiv(H, CS_PH), cdiv(G, CS_GC));
+        const float *src = in;
+        for (int it = 0; it < iters; it++) {
+            k_cbca_rows<<<sgrid, CS_THREADS, 0, s>>>(reinterpret_cast<const float4 *>(src), reinterpret_cast<float4 *>(scratch),
+                                                      reinterpret_cast<const uchar4 *>(arms), G, H, W);
+            MCCNN_LAUNCHED("cbca_rows");
+            k_cbca_cols<<<sgrid, CS_THREADS, 0, s>>>(reinterpret_cast<const float4 *>(scratch), reinterpret_cast<float4 *>(out),
+                                                      reinterpret_cast<const uchar4 *>(arms), count, G, H, W);
+            MCCNN_LAUNCHED("cbca_cols");
+            src = out;
+        }
         return MCCNN_OK;
     }
     // ping-pong so that the last round lands in `out`

@@ -31,7 +31,7 @@ __all__ = ["compute_features", "compute_cost_volume", "cost_volume_aggregation",
 #       from the reference only by float32 re-association (~1e-7 relative);
 #   1 = "exact": the reference's flat running sum over the whole region (pf:157-161), bit-identical
 #       to the reference, <= 729 additions per cell.
-CBCA_SEPARABLE, CBCA_EXACT = 0, 1
+CBCA_SEPARABLE, CBCA_EXACT, CBCA_SEPARABLE_TILED = 0, 1, 2
 CBCA_MODE = CBCA_SEPARABLE
 
 
@@ -261,11 +261,13 @@ def _cbca_one(hwd, D, arms, count, iters, dist, out=None, scratch=None, mode=Non
     H, W, _ = hwd.shape
     if out is None:
         out = _empty_hwd(H, W, D)
-    if scratch is None and iters >= 2:
+    if mode is None:
+        mode = CBCA_MODE
+    if mode == CBCA_SEPARABLE_TILED and int(dist) > 14:     # the tiled kernel's halo is sized for match.py's distance (14)
+        mode = CBCA_SEPARABLE
+    if scratch is None and iters >= (1 if mode == CBCA_SEPARABLE else 2):
         scratch = _empty_hwd(H, W, D)
-    if mode is None:        # the separable kernel's halo is sized for match.py's distance (14); longer arms take the flat walk
-        mode = CBCA_MODE if int(dist) <= 14 else CBCA_EXACT
-    if workspace is None and mode == CBCA_SEPARABLE:
+    if workspace is None and mode == CBCA_SEPARABLE_TILED:
         workspace = cbca_workspace(H, W)
     _ffi.call("mccnn_cbca", _ffi.ptr(hwd), _ffi.ptr(out), _ffi.ptr(scratch), _ffi.ptr(arms), _ffi.ptr(count),
               D, int(H), int(W), int(iters), int(dist), int(mode), _ffi.ptr(workspace), _ffi.stream_ptr())
@@ -283,7 +285,7 @@ def cost_volume_aggregation(left_image, right_image, left_cost_volume, right_cos
         arms, count = cross_arms(image, intensity_threshold, distance_threshold)      # pf:120-121
         hwd, D, H, W = _as_hwd(vol)
         assert tuple(count.shape) == (H, W), "image and cost volume shapes differ"
-        if iters >= 2 and (scratch is None or scratch.shape != hwd.shape):
+        if iters >= 1 and (scratch is None or scratch.shape != hwd.shape):
             scratch = _empty_hwd(H, W, D)
         out = _cbca_one(hwd, D, arms, count, iters, int(distance_threshold), scratch=scratch)
         outs.append(_ret_volume(out, D, vol))
