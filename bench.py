@@ -263,11 +263,13 @@ def run_ours(args):
         hp = m.hp
         it1, it2 = int(hp["cbca_num_iterations1"]), int(hp["cbca_num_iterations2"])
         # algorithmic bytes per stage and launches of the stage's main kernel
+        # ("launch" of a CBCA round = its two streaming passes k_cbca_rows + k_cbca_cols on one volume; the
+        #  algorithmic figure is the fused minimum of 8 B/cell/round, the two passes actually move 16 B/cell)
         model = {
-            "cost_volume": ((8.0 + 512.0 / D) * cells, 1, "k_cost_volume"),
-            "cbca1": (8.0 * cells * it1 * 2, it1 * 2, "k_cbca_round"),
+            "cost_volume": ((8.0 + 512.0 / D) * cells, 1, "k_cost_volume_tc (+k_cost_fill)"),
+            "cbca1": (8.0 * cells * it1 * 2, it1 * 2, "k_cbca_rows+k_cbca_cols"),
             "sgm": (8.0 * cells * 4 * 2, 4, "k_sgm_pass"),
-            "cbca2": (8.0 * cells * it2 * 2, it2 * 2, "k_cbca_round"),
+            "cbca2": (8.0 * cells * it2 * 2, it2 * 2, "k_cbca_rows+k_cbca_cols"),
             "wta": (4.0 * cells * 2, 2, "k_wta"),
         }
         kernels = {}
@@ -278,13 +280,20 @@ def run_ours(args):
                                "achieved_GBps": gbs, "frac_of_hbm_peak": gbs / peak}
         if "features" in acc:
             fl = 2.0 * H * W * 296064.0
-            kernels["features"] = {"kernel": "k_conv64", "ms": acc["features"], "TFLOPs": fl / 1e12,
+            kernels["features"] = {"kernel": "k_conv64_tc (tcgen05 tf32 x3)", "ms": acc["features"], "TFLOPs": fl / 1e12,
                                    "achieved_TFLOPps": fl / (acc["features"] * 1e-3) / 1e12}
+        # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture
+        traffic = {}
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        except Exception:
+            pass
         dom = max((k for k in kernels if k in model), key=lambda k: acc[k])
         nbytes, nl, kname = model[dom]
         roofline = {"bound": "hbm", "kernel": kname, "stage": dom, "achieved": kernels[dom]["achieved_GBps"],
                     "peak": peak, "unit": "GB/s", "frac": kernels[dom]["achieved_GBps"] / peak,
-                    "traffic": None, "peak_source": peak_src,
+                    "traffic": (traffic.get(dom) or {}).get("bytes_per_launch") if (H, W, D) == (1024, 1024, 192) else None,
+                    "traffic_source": (traffic.get(dom) or {}).get("source"), "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": nbytes / nl, "avg_launch_ms": acc[dom] / nl}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,

@@ -10,4 +10,4 @@ from . import process_functional        # noqa: F401
 from . import model                     # noqa: F401
 from . import pipeline                  # noqa: F401
 from .model import NET                  # noqa: F401
-from .pipeline import StereoMatcher, match_pair, DEFAULTS   # noqa: F401
+from .pipeline import StereoMatcher, match_pair, shard_window, DEFAULTS   # noqa: F401

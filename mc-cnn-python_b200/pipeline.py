@@ -239,6 +239,16 @@ class StereoMatcher(object):
         return _pf._hwd_view(self.final_volume[which], self.D)
 
 
+def shard_window(num_pairs, rank, world_size):
+    """[start, end) of the pair indices rank `rank` processes: the reference's only parallel mode, disjoint
+    `-s/--start`, `-e/--end` windows per process (match.py:26-28, :85-90), made deterministic from (rank, world)."""
+    num_pairs, rank, world_size = int(num_pairs), int(rank), int(world_size)
+    assert 0 <= rank < world_size and num_pairs >= 0
+    base, extra = divmod(num_pairs, world_size)
+    start = rank * base + min(rank, extra)
+    return start, start + base + (1 if rank < extra else 0)
+
+
 def match_pair(left_image, right_image, ndisp, checkpoint=None, **hp):
     """match.py:131-175 for one pair: normalised images [H,W,1] -> final left disparity map [H,W]."""
     a = left_image

@@ -189,6 +189,27 @@ def test_cbca_separable_vs_golden_and_oracle(pf, oracle, pipeline_golden):
     assert eq(Lg, Lo)
 
 
+def test_cbca_tiled_tma_mode_matches_streaming_mode_and_oracle(pf, oracle, monkeypatch):
+    """MCCNN_CBCA_SEPARABLE_TILED (fused TMA-staged kernel) forms the same sums in the same order as the default
+    two-pass mode: identical results, and both within the re-association tolerance of the oracle.  Covers flat
+    images (13-pixel arms: sub-slab fallback levels), ragged sizes, small and odd granule counts."""
+    for (H, W, D, levels, iters) in [(40, 90, 70, 4, 3), (33, 47, 192, 30, 2), (37, 29, 5, 1, 2), (50, 21, 33, 2, 3),
+                                      (64, 64, 12, 1, 1), (17, 200, 9, 3, 2)]:
+        li, ri = synth_images(H * W + D, H, W, levels, 2)
+        rng = np.random.default_rng(D)
+        Lv = rng.standard_normal((D, H, W)).astype(np.float32) * 50
+        Rv = rng.standard_normal((D, H, W)).astype(np.float32) * 50
+        monkeypatch.setattr(pf, "CBCA_MODE", pf.CBCA_SEPARABLE)
+        Ls, Rs = pf.cost_volume_aggregation(li, ri, Lv, Rv, 0.02, 14, iters)
+        monkeypatch.setattr(pf, "CBCA_MODE", pf.CBCA_SEPARABLE_TILED)
+        Lt, Rt = pf.cost_volume_aggregation(li, ri, Lv, Rv, 0.02, 14, iters)
+        assert eq(Ls, Lt) and eq(Rs, Rt), (H, W, D)
+        Lo, Ro = oracle.cost_volume_aggregation(li, ri, Lv, Rv, 0.02, 14, iters)
+        scale = float(np.abs(Lo).max())
+        np.testing.assert_allclose(Lt, Lo, atol=CBCA_SEP_RTOL * scale, rtol=0)
+        np.testing.assert_allclose(Rt, Ro, atol=CBCA_SEP_RTOL * scale, rtol=0)
+
+
 def test_cbca_plane_constant_is_fixed_point(pf):
     """Property (any size): a volume that is constant per disparity plane with small-integer values is a
     fixed point of region averaging (exact sums, exact division)."""
