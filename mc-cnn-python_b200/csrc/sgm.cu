@@ -63,8 +63,19 @@ __device__ __forceinline__ int f2key(float x) {
 }
 __device__ __forceinline__ float key2f(int k) { return __int_as_float(k ^ ((k >> 31) & 0x7fffffff)); }
 
-template <int JP, int PF>
+__device__ __forceinline__ void sgm_cp_async16(void *smem_dst, const void *gmem_src) {
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem_src));
+}
+
+// JP granules per lane, PF = look-ahead (steps) of the flag register ring, CP = slots of the shared-memory cell ring
+// (cells are fetched CP - 1 steps ahead with cp.async: the pass is bound by bytes in flight -- there are only H or
+// W scanlines x 2 volumes = 2048 warps on the whole chip -- and a ring in shared memory buys look-ahead that
+// registers cannot).
+template <int JP, int PF, int CP>
 __global__ void __launch_bounds__(32, 16) k_sgm_pass(const __grid_constant__ SgmParams prm) {
+    __shared__ float4 cring[CP][JP][32];
+    constexpr int DIST = CP - 1;
     const SgmJob job = prm.job[blockIdx.y];
     const int lane = threadIdx.x;
     const int line = blockIdx.x;
@@ -89,49 +100,89 @@ __global__ void __launch_bounds__(32, 16) k_sgm_pass(const __grid_constant__ Sgm
     const int src_up = (lane >= NLg - 1) ? 0 : lane + 1;
     const bool first_lane = (lane == 0), last_lane = (lane == NLg - 1);
 
-    auto load_cells = [&](int t, float4 (&dst)[JP]) {
-        const long long p = p0 + (long long)t * pstride;
+    auto fix_ragged = [&](float4 &v, int j) {
+        if (ragged) {
+            int d = g[j] << 2;
+            if (d + 1 >= D) v.y = INF;
+            if (d + 2 >= D) v.z = INF;
+            if (d + 3 >= D) v.w = INF;
+        }
+    };
+    // cells of step t -> ring slot t % CP (one cp.async group per step, empty past the end of the scanline)
+    auto prefetch_cells = [&](int t) {
+        if (t < N) {
+            const long long p = p0 + (long long)t * pstride;
+            const int slot = t % CP;
+#pragma unroll
+            for (int j = 0; j < JP; j++)
+                if (gv[j]) sgm_cp_async16(&cring[slot][j][lane], &vol4[p * G + g[j]]);
+        }
+        asm volatile("cp.async.commit_group;\n" ::: "memory");
+    };
+    auto take_cells = [&](int t, float4 (&dst)[JP]) {
+        const int slot = t % CP;
 #pragma unroll
         for (int j = 0; j < JP; j++) {
             float4 v = make_float4(INF, INF, INF, INF);
             if (gv[j]) {
-                v = vol4[p * G + g[j]];
-                if (ragged) {
-                    int d = g[j] << 2;
-                    if (d + 1 >= D) v.y = INF;
-                    if (d + 2 >= D) v.z = INF;
-                    if (d + 3 >= D) v.w = INF;
-                }
+                v = cring[slot][j][lane];
+                fix_ragged(v, j);
             }
             dst[j] = v;
         }
     };
-    // 4-bit penalty selectors of this lane's granules at step t (bit k <-> d = 4g + k), own flag in bit 31
-    auto load_flags = [&](int t, uint32_t (&dst)[JP], uint32_t &own) {
-        const int hb = h0 + t * dh + hoff, wb = w0 + t * dw + woff;
+    // Penalty selectors of step t.  The ring keeps the RAW bit-map words (loaded PF steps ahead) and the 4-bit
+    // selectors of this lane's granules (bit k <-> d = 4g + k) are extracted only when the step is executed, so
+    // that the loads are never waited for at issue.
+    struct FlagWords { uint32_t lo[JP], hi[JP], own; };
+    auto flag_pos = [&](int t, int &pos1) {
+        const int wb = w0 + t * dw + woff;
+        pos1 = prm.PADW * 32 + wb;
+        return h0 + t * dh + hoff;
+    };
+    auto load_flags = [&](int t, FlagWords &fw) {
+        int pos1;
+        const int hb = flag_pos(t, pos1);
         const uint32_t *orow = job.oth_map + (size_t)hb * WR;
-        const int pos1 = prm.PADW * 32 + wb;
-        own = (job.own_map[(size_t)hb * WR + (pos1 >> 5)] >> (pos1 & 31)) & 1u;
+        fw.own = job.own_map[(size_t)hb * WR + (pos1 >> 5)];
 #pragma unroll
         for (int j = 0; j < JP; j++) {
-            uint32_t f = 0;
+            fw.lo[j] = 0; fw.hi[j] = 0;
             if (gv[j]) {
-                if (job.is_left) {
-                    int pos = pos1 - 4 * g[j] - 3;                 // x = wb - d, d = 4g+3 .. 4g
-                    f = __funnelshift_r(orow[pos >> 5], orow[(pos >> 5) + 1], pos & 31) & 15u;
-                    f = __brev(f) >> 28;
-                } else {
-                    int pos = pos1 + 4 * g[j];                     // x = wb + d
-                    f = __funnelshift_r(orow[pos >> 5], orow[(pos >> 5) + 1], pos & 31) & 15u;
-                }
+                const int pos = job.is_left ? pos1 - 4 * g[j] - 3 : pos1 + 4 * g[j];   // x = wb - d (d = 4g+3 .. 4g) | x = wb + d
+                fw.lo[j] = orow[pos >> 5];
+                fw.hi[j] = orow[(pos >> 5) + 1];
             }
+        }
+    };
+    auto extract_flags = [&](int t, const FlagWords &fw, uint32_t (&dst)[JP], uint32_t &own) {
+        int pos1;
+        (void)flag_pos(t, pos1);
+        own = (fw.own >> (pos1 & 31)) & 1u;
+#pragma unroll
+        for (int j = 0; j < JP; j++) {
+            const int pos = job.is_left ? pos1 - 4 * g[j] - 3 : pos1 + 4 * g[j];
+            uint32_t f = __funnelshift_r(fw.lo[j], fw.hi[j], pos & 31) & 15u;
+            if (job.is_left) f = __brev(f) >> 28;
             dst[j] = f;
         }
     };
 
     // step 0: the first pixel of the scanline is left unchanged (pf:485-501) and seeds the recurrence
     float4 prev[JP];
-    load_cells(0, prev);
+    {
+#pragma unroll
+        for (int j = 0; j < JP; j++) {
+            float4 v = make_float4(INF, INF, INF, INF);
+            if (gv[j]) {
+                v = vol4[p0 * G + g[j]];
+                fix_ragged(v, j);
+            }
+            prev[j] = v;
+        }
+    }
+#pragma unroll 1
+    for (int t = 1; t <= DIST; t++) prefetch_cells(t);
     float m;
     {
         float lm = INF;
@@ -140,12 +191,10 @@ __global__ void __launch_bounds__(32, 16) k_sgm_pass(const __grid_constant__ Sgm
         m = key2f(__reduce_min_sync(0xffffffffu, f2key(lm)));
     }
 
-    float4 ring[PF][JP];
-    uint32_t fring[PF][JP];
-    uint32_t oring[PF];
+    FlagWords fring[PF];
 #pragma unroll
     for (int u = 0; u < PF; u++)
-        if (1 + u < N) { load_cells(1 + u, ring[u]); load_flags(1 + u, fring[u], oring[u]); }
+        if (1 + u < N) load_flags(1 + u, fring[u]);
 
     for (int t0 = 1; t0 < N; t0 += PF) {
 #pragma unroll
@@ -155,9 +204,12 @@ __global__ void __launch_bounds__(32, 16) k_sgm_pass(const __grid_constant__ Sgm
                 float4 cur[JP];
                 uint32_t fb[JP];
 #pragma unroll
-                for (int j = 0; j < JP; j++) { cur[j] = ring[u][j]; fb[j] = fring[u][j]; }
-                const uint32_t f1 = oring[u];
-                if (t + PF < N) { load_cells(t + PF, ring[u]); load_flags(t + PF, fring[u], oring[u]); }
+                uint32_t f1;
+                extract_flags(t, fring[u], fb, f1);
+                if (t + PF < N) load_flags(t + PF, fring[u]);
+                asm volatile("cp.async.wait_group %0;\n" ::"n"(DIST - 1) : "memory");     // the cells of step t have landed
+                take_cells(t, cur);
+                prefetch_cells(t + DIST);                                                  // into the slot step t - 1 used
 
                 // penalties (pf:535-541): f1 = (D1 >= tauD), per-cell bit = (D2 >= tauD)
                 const float pa1 = f1 ? prm.P1q1 : prm.P1, pb1 = f1 ? prm.P1q2 : prm.P1q1;
@@ -196,10 +248,10 @@ static int launch_pass(const SgmParams &prm, int njobs, cudaStream_t s) {
     const bool horizontal = (prm.rh == 0);
     dim3 grid(horizontal ? prm.H : prm.W, njobs), block(32);
     switch (JP) {
-        case 1: k_sgm_pass<1, 6><<<grid, block, 0, s>>>(prm); break;
-        case 2: k_sgm_pass<2, 4><<<grid, block, 0, s>>>(prm); break;
-        case 3: k_sgm_pass<3, 3><<<grid, block, 0, s>>>(prm); break;
-        case 4: k_sgm_pass<4, 2><<<grid, block, 0, s>>>(prm); break;
+        case 1: k_sgm_pass<1, 4, 16><<<grid, block, 0, s>>>(prm); break;
+        case 2: k_sgm_pass<2, 4, 12><<<grid, block, 0, s>>>(prm); break;
+        case 3: k_sgm_pass<3, 3, 8><<<grid, block, 0, s>>>(prm); break;
+        case 4: k_sgm_pass<4, 2, 8><<<grid, block, 0, s>>>(prm); break;
         default:
             set_error("sgm: ndisp %d too large (max 512)", prm.D);
             return MCCNN_ERR_UNSUPPORTED;
