@@ -11,7 +11,7 @@ namespace mccnn {
 // first minimum (strict <), then the group merges lexicographically on (value, d).
 // HBM-bound: 4 B per cell read once, fully coalesced (a warp reads 512 contiguous bytes).
 // ------------------------------------------------------------------------------------------
-template <int GS>
+template <int GS, int NL>
 __global__ void __launch_bounds__(256) k_wta(const float *__restrict__ vol, float *__restrict__ disp,
                                              int D, int Dp, long long P) {
     const int lane_in_group = threadIdx.x % GS;
@@ -22,13 +22,28 @@ __global__ void __launch_bounds__(256) k_wta(const float *__restrict__ vol, floa
     if (live) {
         const float4 *row = reinterpret_cast<const float4 *>(vol + p * Dp);
         const int G = Dp >> 2;
-        for (int g = lane_in_group; g < G; g += GS) {
-            float4 v = __ldcs(row + g);
+        // all of this lane's granules first (NL independent 16-byte loads in flight), then the compares
+        float4 v[NL];
+#pragma unroll
+        for (int i = 0; i < NL; i++) {
+            const int g = lane_in_group + i * GS;
+            v[i] = g < G ? __ldcs(row + g) : make_float4(CUDART_INF_F, CUDART_INF_F, CUDART_INF_F, CUDART_INF_F);
+        }
+#pragma unroll
+        for (int i = 0; i < NL; i++) {
+            const int d = (lane_in_group + i * GS) << 2;
+            if (d + 0 < D && v[i].x < best) { best = v[i].x; bd = d; }
+            if (d + 1 < D && v[i].y < best) { best = v[i].y; bd = d + 1; }
+            if (d + 2 < D && v[i].z < best) { best = v[i].z; bd = d + 2; }
+            if (d + 3 < D && v[i].w < best) { best = v[i].w; bd = d + 3; }
+        }
+        for (int g = lane_in_group + NL * GS; g < G; g += GS) {                // (only for ndisp beyond NL * GS * 4)
+            float4 w = __ldcs(row + g);
             int d = g << 2;
-            if (d + 0 < D && v.x < best) { best = v.x; bd = d; }
-            if (d + 1 < D && v.y < best) { best = v.y; bd = d + 1; }
-            if (d + 2 < D && v.z < best) { best = v.z; bd = d + 2; }
-            if (d + 3 < D && v.w < best) { best = v.w; bd = d + 3; }
+            if (d + 0 < D && w.x < best) { best = w.x; bd = d; }
+            if (d + 1 < D && w.y < best) { best = w.y; bd = d + 1; }
+            if (d + 2 < D && w.z < best) { best = w.z; bd = d + 2; }
+            if (d + 3 < D && w.w < best) { best = w.w; bd = d + 3; }
         }
     }
 #pragma unroll
@@ -202,12 +217,12 @@ int mccnn_wta(const float *vol, float *disp, int D, int H, int W, void *stream) 
     int Dp = dpitch(D), G = Dp / 4;
     cudaStream_t s = (cudaStream_t)stream;
     const int T = 256;
-#define WTA_CASE(GS) k_wta<GS><<<cdiv(P * GS, T), T, 0, s>>>(vol, disp, D, Dp, P)
-    if (G >= 24) WTA_CASE(32);
-    else if (G >= 12) WTA_CASE(16);
-    else if (G >= 6) WTA_CASE(8);
-    else if (G >= 3) WTA_CASE(4);
-    else WTA_CASE(2);
+#define WTA_CASE(GS, NL) k_wta<GS, NL><<<cdiv(P * GS, T), T, 0, s>>>(vol, disp, D, Dp, P)
+    if (G > 64) WTA_CASE(32, 4);
+    else if (G >= 12) WTA_CASE(16, 4);
+    else if (G >= 6) WTA_CASE(8, 2);
+    else if (G >= 3) WTA_CASE(4, 2);
+    else WTA_CASE(2, 1);
 #undef WTA_CASE
     MCCNN_LAUNCHED("wta");
     return MCCNN_OK;
