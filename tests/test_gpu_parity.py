@@ -423,3 +423,43 @@ def test_full_pipeline_recovers_known_shift(pkg):
     assert d.shape == (H, W) and d.dtype == np.float32
     inner = d[8:-8, 40:-8]
     assert np.mean(np.abs(inner - shift) < 0.5) > 0.95, float(np.mean(np.abs(inner - shift) < 0.5))
+
+
+# ------------------------------------------------------------------------------------------ match.py drop-in
+def test_match_cli_writes_middlebury_outputs(pkg, tmp_path):
+    """The match.py drop-in: list file + calib + images in, PFM / PGM / time file out (match.py:46-54, :182-184),
+    identical to match_pair on the same pair; -s/-e window respected."""
+    import importlib
+    cv2 = pytest.importorskip("cv2")
+    match = importlib.import_module("mc-cnn-python_b200.match")
+    util = importlib.import_module("mc-cnn-python_b200.util")
+    data = tmp_path / "data"
+    H, W, D = 40, 72, 16
+    rng = np.random.default_rng(5)
+    paths = []
+    for name in ("A", "B", "C"):
+        d = data / name
+        d.mkdir(parents=True)
+        base = rng.integers(0, 256, (H, W + 4)).astype(np.uint8)
+        base = cv2.GaussianBlur(base, (5, 5), 1.0)
+        cv2.imwrite(str(d / "im0.png"), base[:, :W])
+        cv2.imwrite(str(d / "im1.png"), base[:, 4:])
+        (d / "calib.txt").write_text("cam0=[]\ncam1=[]\ndoffs=0\nbaseline=1\nwidth=%d\nheight=%d\nndisp=%d\n" % (W, H, D))
+        paths.append(str(d / "im0.png"))
+    lst = tmp_path / "list.txt"
+    lst.write_text("\n".join(paths) + "\n")
+    save = tmp_path / "out"
+    save.mkdir()
+    done = match.main(["--list_file", str(lst), "--data_dir", str(data), "--save_dir", str(save), "-t", "x",
+                       "-s", "1", "-e", "2"])
+    assert done == [1, 2]
+    assert not (save / "submit_x" / "A").exists()
+    for name in ("B", "C"):
+        res = save / "submit_x" / name
+        pfm = util.readPfm(str(res / "disp0MCCNN.pfm"))
+        assert pfm.shape == (H, W) and float((res / "timeMCCNN.txt").read_text()) > 0
+        assert (save / "submit_x_imgs" / name / "disp0MCCNN.pgm").read_bytes().startswith(b"P5")
+        li = match.read_normalised(str(data / name / "im0.png"))
+        ri = match.read_normalised(str(data / name / "im1.png"))
+        ref = pkg.match_pair(li, ri, D)
+        assert eq(pfm, ref)
