@@ -143,10 +143,47 @@ __global__ void k_subpixel(const float *__restrict__ disp, const float *__restri
 // a11  median_filter (pf:403-421): border-clipped window, np.median.
 // ------------------------------------------------------------------------------------------
 #define MCCNN_MAX_WINDOW 121
+// median of 25 NaN-free values held in registers: 99 compare-exchanges (Devillard's opt_med25 selection network,
+// checked against np.median), no local memory
+__device__ __forceinline__ float median25(float (&p)[25]) {
+#define MCCNN_CX(a, b) { const float lo_ = fminf(p[a], p[b]), hi_ = fmaxf(p[a], p[b]); p[a] = lo_; p[b] = hi_; }
+    MCCNN_CX(0, 1) MCCNN_CX(3, 4) MCCNN_CX(2, 4) MCCNN_CX(2, 3) MCCNN_CX(6, 7) MCCNN_CX(5, 7) MCCNN_CX(5, 6) MCCNN_CX(9, 10)
+    MCCNN_CX(8, 10) MCCNN_CX(8, 9) MCCNN_CX(12, 13) MCCNN_CX(11, 13) MCCNN_CX(11, 12) MCCNN_CX(15, 16) MCCNN_CX(14, 16)
+    MCCNN_CX(14, 15) MCCNN_CX(18, 19) MCCNN_CX(17, 19) MCCNN_CX(17, 18) MCCNN_CX(21, 22) MCCNN_CX(20, 22) MCCNN_CX(20, 21)
+    MCCNN_CX(23, 24) MCCNN_CX(2, 5) MCCNN_CX(3, 6) MCCNN_CX(0, 6) MCCNN_CX(0, 3) MCCNN_CX(4, 7) MCCNN_CX(1, 7) MCCNN_CX(1, 4)
+    MCCNN_CX(11, 14) MCCNN_CX(8, 14) MCCNN_CX(8, 11) MCCNN_CX(12, 15) MCCNN_CX(9, 15) MCCNN_CX(9, 12) MCCNN_CX(13, 16)
+    MCCNN_CX(10, 16) MCCNN_CX(10, 13) MCCNN_CX(20, 23) MCCNN_CX(17, 23) MCCNN_CX(17, 20) MCCNN_CX(21, 24) MCCNN_CX(18, 24)
+    MCCNN_CX(18, 21) MCCNN_CX(19, 22) MCCNN_CX(8, 17) MCCNN_CX(9, 18) MCCNN_CX(0, 18) MCCNN_CX(0, 9) MCCNN_CX(10, 19)
+    MCCNN_CX(1, 19) MCCNN_CX(1, 10) MCCNN_CX(11, 20) MCCNN_CX(2, 20) MCCNN_CX(2, 11) MCCNN_CX(12, 21) MCCNN_CX(3, 21)
+    MCCNN_CX(3, 12) MCCNN_CX(13, 22) MCCNN_CX(4, 22) MCCNN_CX(4, 13) MCCNN_CX(14, 23) MCCNN_CX(5, 23) MCCNN_CX(5, 14)
+    MCCNN_CX(15, 24) MCCNN_CX(6, 24) MCCNN_CX(6, 15) MCCNN_CX(7, 16) MCCNN_CX(7, 19) MCCNN_CX(13, 21) MCCNN_CX(15, 23)
+    MCCNN_CX(7, 13) MCCNN_CX(7, 15) MCCNN_CX(1, 9) MCCNN_CX(3, 11) MCCNN_CX(5, 17) MCCNN_CX(11, 17) MCCNN_CX(9, 17)
+    MCCNN_CX(4, 10) MCCNN_CX(6, 12) MCCNN_CX(7, 14) MCCNN_CX(4, 6) MCCNN_CX(4, 7) MCCNN_CX(12, 14) MCCNN_CX(10, 14)
+    MCCNN_CX(6, 7) MCCNN_CX(10, 12) MCCNN_CX(6, 10) MCCNN_CX(6, 17) MCCNN_CX(12, 17) MCCNN_CX(7, 17) MCCNN_CX(7, 10)
+    MCCNN_CX(12, 18) MCCNN_CX(7, 12) MCCNN_CX(10, 18) MCCNN_CX(12, 20) MCCNN_CX(10, 20) MCCNN_CX(10, 12)
+#undef MCCNN_CX
+    return p[12];
+}
+
 __global__ void k_median(const float *__restrict__ in, float *__restrict__ out, int H, int W, int rh, int rw) {
     int w = blockIdx.x * blockDim.x + threadIdx.x;
     int h = blockIdx.y * blockDim.y + threadIdx.y;
     if (w >= W || h >= H) return;
+    if (rh == 2 && rw == 2 && h >= 2 && h + 2 < H && w >= 2 && w + 2 < W) {
+        // the common case (match.py:172 uses 5x5): a full window in registers
+        float p[25];
+        bool nan = false;
+#pragma unroll
+        for (int y = 0; y < 5; y++)
+#pragma unroll
+            for (int x = 0; x < 5; x++) {
+                const float v = in[(size_t)(h + y - 2) * W + (w + x - 2)];
+                p[y * 5 + x] = v;
+                nan |= (v != v);
+            }
+        out[(size_t)h * W + w] = nan ? CUDART_NAN_F : median25(p);
+        return;
+    }
     float buf[MCCNN_MAX_WINDOW];
     int hs = max(h - rh, 0), he = min(h + rh + 1, H);
     int ws = max(w - rw, 0), we = min(w + rw + 1, W);
