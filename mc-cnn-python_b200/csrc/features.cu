@@ -59,7 +59,11 @@ __global__ void __launch_bounds__(256) k_conv1(const float *__restrict__ img, co
 // 0 / 1 / 2 pixels (the 128B swizzle is a function of the absolute shared-memory address, so a start that
 // is not 1024-byte aligned needs no base offset -- checked on the device), which is why a tile yields 126
 // pixels, not 128.  Consecutive tiles visit the channel blocks in opposite order, so the weights are
-// reloaded once per tile, not twice.
+// reloaded once per tile, not twice.  An input row feeds up to three output rows (one per kernel row); the
+// weights of a kernel column are stacked by kernel row in shared memory and the accumulators of consecutive
+// output rows are adjacent in TMEM, so ONE tcgen05.mma with N = 64 / 128 / 192 updates all of them -- small-N
+// MMAs do not run proportionally faster, so this halves the MMA count and the time.  Accumulators are zeroed
+// through tcgen05.st by the epilogue, so every MMA accumulates.
 //   warp 0: MMA issue (one lane); warp 1: TMA producer (one lane); warps 2-7: operand split;
 //   warps 8-15: epilogue -- bias, ReLU or (last layer) channel L2 normalisation, 256-bit stores.
 // ------------------------------------------------------------------------------------------
@@ -72,9 +76,9 @@ constexpr int CT_THREADS = 512;
 constexpr int CT_NSPLIT = 192;
 
 struct __align__(1024) CtcSmem {
-    unsigned char w[9][2][CT_WBLK_BYTES];        // [tap][hi, lo]
+    unsigned char w[2][3][3][CT_WBLK_BYTES];     // [hi, lo][kx][2 - ky]: the three kernel rows of a column stacked, ky descending
     unsigned char a_hi[2][CT_ROW_BYTES], a_lo[2][CT_ROW_BYTES];
-    unsigned long long bar_w, bar_row[2], bar_rowdone[2], bar_full[2], bar_empty[2];
+    unsigned long long bar_w, bar_row[2], bar_rowdone[2], bar_full[2], bar_empty[2], bar_zero;
     unsigned tmem_base;
 };
 
@@ -107,6 +111,7 @@ k_conv64_tc(const __grid_constant__ CtcMaps maps, const float *__restrict__ bias
     }
     if (tid == 32) {
         tc_mbar_init(&sm.bar_w, 1);
+        tc_mbar_init(&sm.bar_zero, 1);
         for (int i = 0; i < 2; i++) {
             tc_mbar_init(&sm.bar_row[i], 1);
             tc_mbar_init(&sm.bar_rowdone[i], 1);
@@ -119,8 +124,8 @@ k_conv64_tc(const __grid_constant__ CtcMaps maps, const float *__restrict__ bias
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
     const unsigned tmem_base = sm.tmem_base;
-    // instruction descriptor: D = F32, A = B = TF32, both K-major, N = 64, M = 128
-    const unsigned idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((unsigned)(F >> 3) << 17) | ((unsigned)(128 >> 4) << 24);
+    // instruction descriptor: D = F32, A = B = TF32, both K-major, M = 128; N (64, 128 or 192) is filled in per MMA
+    const unsigned idesc_base = (1u << 4) | (2u << 7) | (2u << 10) | ((unsigned)(128 >> 4) << 24);
     constexpr int NROW = CT_ROWS + 2;           // input rows per tile
 
     // A tile visits the channel blocks in the order (t & 1), (t & 1) ^ 1, so the block the previous tile ended with
@@ -143,8 +148,8 @@ k_conv64_tc(const __grid_constant__ CtcMaps maps, const float *__restrict__ bias
                         }
                         tc_mbar_expect_tx(&sm.bar_w, CT_W_BYTES);
                         for (int tap = 0; tap < 9; tap++) {
-                            tc_tma_load_3d(sm.w[tap][0], &maps.whi, kb * 32, 0, tap, &sm.bar_w);
-                            tc_tma_load_3d(sm.w[tap][1], &maps.wlo, kb * 32, 0, tap, &sm.bar_w);
+                            tc_tma_load_3d(sm.w[0][tap % 3][2 - tap / 3], &maps.whi, kb * 32, 0, tap, &sm.bar_w);
+                            tc_tma_load_3d(sm.w[1][tap % 3][2 - tap / 3], &maps.wlo, kb * 32, 0, tap, &sm.bar_w);
                         }
                         resident = kb;
                         wloads++;
@@ -182,27 +187,28 @@ k_conv64_tc(const __grid_constant__ CtcMaps maps, const float *__restrict__ bias
                     if (tid == 0) {
                         if (new_weights && r == 0) { tc_mbar_wait(&sm.bar_w, wloads & 1); }
                         if (bi == 0 && r == 0 && tt >= 2) tc_mbar_wait(&sm.bar_empty[abuf], ((tt >> 1) - 1) & 1);
+                        if (rr == 0) tc_mbar_wait(&sm.bar_zero, 0);
                         asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
                         const unsigned long long ah = tc_smem_desc(tc_smem_u32(sm.a_hi[rb])), al = tc_smem_desc(tc_smem_u32(sm.a_lo[rb]));
+                        // Input row r feeds accumulator j = r - ky for every kernel row ky it can pair with: the weights
+                        // of those kernel rows are stacked (ky descending = j ascending), so ONE MMA with N = 64, 128 or
+                        // 192 updates the adjacent accumulators j = r - kymax .. r - kymin.  Accumulators start from the
+                        // zeros the epilogue leaves in TMEM, so every MMA accumulates.
+                        const int kymax = min(2, r), kymin = max(0, r - (CT_ROWS - 1));
+                        const unsigned nacc = (unsigned)(kymax - kymin + 1);
+                        const unsigned idesc_n = idesc_base | ((nacc * F >> 3) << 17);
+                        const unsigned d_tmem = tmem_base + abuf * (CT_ROWS * F) + (unsigned)(r - kymax) * F;
 #pragma unroll
-                        for (int j = 0; j < CT_ROWS; j++) {
-                            const int ky = r - j;
-                            if (ky < 0 || ky > 2) continue;
-                            const unsigned d_tmem = tmem_base + abuf * (CT_ROWS * F) + j * F;
+                        for (int kx = 0; kx < 3; kx++) {
+                            const unsigned long long wh = tc_smem_desc(tc_smem_u32(sm.w[0][kx][2 - kymax]));
+                            const unsigned long long wl = tc_smem_desc(tc_smem_u32(sm.w[1][kx][2 - kymax]));
 #pragma unroll
-                            for (int kx = 0; kx < 3; kx++) {
-                                const int tap = ky * 3 + kx;
-                                const unsigned long long wh = tc_smem_desc(tc_smem_u32(sm.w[tap][0])), wl = tc_smem_desc(tc_smem_u32(sm.w[tap][1]));
-#pragma unroll
-                                for (int ks = 0; ks < 4; ks++) {
-                                    const unsigned long long aoff = (unsigned long long)((kx * 128 + ks * 32) >> 4);
-                                    const unsigned long long woff = (unsigned long long)((ks * 32) >> 4);
-                                    // first MMA into accumulator j of this tile: first block, tap (0,0), first K step
-                                    const unsigned acc = (bi == 0 && ky == 0 && kx == 0 && ks == 0) ? 0u : 1u;
-                                    tc_mma_tf32(d_tmem, ah + aoff, wh + woff, idesc, acc);
-                                    tc_mma_tf32(d_tmem, ah + aoff, wl + woff, idesc, 1);
-                                    tc_mma_tf32(d_tmem, al + aoff, wh + woff, idesc, 1);
-                                }
+                            for (int ks = 0; ks < 4; ks++) {
+                                const unsigned long long aoff = (unsigned long long)((kx * 128 + ks * 32) >> 4);
+                                const unsigned long long woff = (unsigned long long)((ks * 32) >> 4);
+                                tc_mma_tf32(d_tmem, ah + aoff, wh + woff, idesc_n, 1);
+                                tc_mma_tf32(d_tmem, ah + aoff, wl + woff, idesc_n, 1);
+                                tc_mma_tf32(d_tmem, al + aoff, wh + woff, idesc_n, 1);
                             }
                         }
                         tc_mma_commit(&sm.bar_rowdone[rb]);
@@ -217,6 +223,19 @@ k_conv64_tc(const __grid_constant__ CtcMaps maps, const float *__restrict__ bias
         const int q = warp & 3, half = (warp - 8) >> 2;
         const int m = 32 * q + lane;
         const float4 *b4 = reinterpret_cast<const float4 *>(bias);
+        // MMAs only ever accumulate: this warp's share of both accumulator buffers (its lane quarter, its two rows)
+        // starts as zeros and is zeroed again after every read
+        auto zero_acc = [&](unsigned abuf, int j) {
+            const unsigned taddr = tmem_base + ((unsigned)(32 * q) << 16) + abuf * (CT_ROWS * F) + j * F;
+            tc_tmem_st32_zero(taddr);
+            tc_tmem_st32_zero(taddr + 32);
+        };
+        for (unsigned ab = 0; ab < 2; ab++)
+            for (int jj = 0; jj < CT_ROWS / 2; jj++) zero_acc(ab, half * (CT_ROWS / 2) + jj);
+        asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+        tc_named_barrier(2, 256);                       // all eight epilogue warps have zeroed their part ...
+        if (tid == 256) tc_mbar_arrive(&sm.bar_zero);    // ... tell the MMA issuer
         unsigned tt = 0;
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, tt++) {
             const unsigned abuf = tt & 1;
@@ -231,6 +250,7 @@ k_conv64_tc(const __grid_constant__ CtcMaps maps, const float *__restrict__ bias
                 const unsigned taddr = tmem_base + ((unsigned)(32 * q) << 16) + abuf * (CT_ROWS * F) + j * F;
                 tc_tmem_ld32(taddr, v0);
                 tc_tmem_ld32(taddr + 32, v1);
+                zero_acc(abuf, j);
                 float ss = 0.f;
 #pragma unroll
                 for (int o = 0; o < 32; o += 4) {
@@ -274,6 +294,7 @@ k_conv64_tc(const __grid_constant__ CtcMaps maps, const float *__restrict__ bias
                     }
                 }
             }
+            asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");
             asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
             tc_mbar_arrive(&sm.bar_empty[abuf]);
         }

@@ -93,6 +93,16 @@ __device__ __forceinline__ void tc_tmem_ld32(unsigned taddr, unsigned (&v)[32]) 
 }
 
 
+// zero 32 consecutive TMEM columns of this warp's 32 lanes (completion: tcgen05.wait::st)
+__device__ __forceinline__ void tc_tmem_st32_zero(unsigned taddr) {
+    const unsigned z = 0u;
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, "
+        "%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1};\n" ::"r"(taddr), "r"(z)
+        : "memory");
+}
+
 __device__ __forceinline__ unsigned tc_tf32(float x) {
     unsigned r;
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
