@@ -4,7 +4,7 @@
 // (pf:640-650): k_cbca_rows writes Hs, k_cbca_cols adds it along the spine and divides.  Both are pure
 // gathers with no shared memory and no barriers: the lanes of a warp are consecutive disparity granules of
 // one pixel (two pixels when a warp straddles a pixel boundary), so every load and store is a contiguous run
-// and an arm walk is warp uniform; neighbouring pixels are served by L1/L2 (a CTA covers an 8x8 pixel patch
+// and an arm walk is warp uniform; neighbouring pixels are served by L1/L2 (a CTA covers an 8x4 pixel patch
 // per 64 disparities).  HBM traffic is 16 B per cell per round -- twice the fused minimum -- but the passes
 // run near copy speed, which the fused shared-memory kernel (cbca_tile.cuh) does not: its short
 // data-dependent phases are dominated by barrier waits (profiles/r1_cbca_round_tile.md).
@@ -15,7 +15,7 @@
 
 namespace mccnn {
 
-constexpr int CS_PH = 8, CS_PW = 8, CS_GC = 16, CS_THREADS = 256;   // patch 8x8 pixels x 16 granules per CTA
+constexpr int CS_PH = 8, CS_PW = 4, CS_GC = 16, CS_THREADS = 128;   // patch 8x4 pixels x 16 granules per CTA (best of a sweep)
 
 __device__ __forceinline__ void cs_add(float4 &acc, const float4 v) {
     acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
