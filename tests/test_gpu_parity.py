@@ -425,6 +425,84 @@ def test_full_pipeline_recovers_known_shift(pkg):
     assert np.mean(np.abs(inner - shift) < 0.5) > 0.95, float(np.mean(np.abs(inner - shift) < 0.5))
 
 
+# ------------------------------------------------------------------------------------------ BASELINE configs
+def test_config1_full_pipeline_stagewise_vs_oracle(pkg, pf, oracle):
+    """BASELINE config 1 (the correctness gate): 128x128 pair, 32 disparities, random-init MC-CNN-fast features,
+    the whole match.py pipeline.  Features against the CPU oracle; every later stage is fed the oracle's input for
+    that stage (stage-wise gating keeps float near-ties from hiding real differences)."""
+    H, W, D = 128, 128, 32
+    li, ri = synth_images(11, H, W, 40, 3)
+    ws, bs = pf.glorot_uniform_weights(seed=0)
+    fl, fr = pf.compute_features(li, ri, 11, 11, (ws, bs))
+    flo, fro = oracle.compute_features(li, ri, 11, 11, (ws, bs))
+    assert np.abs(fl - flo).max() < FEAT_ATOL and np.abs(fr - fro).max() < FEAT_ATOL
+    do, st = oracle.match_from_features(li, ri, flo, fro, D, return_stages=True)
+    L, R = pf.compute_cost_volume(flo, fro, D)
+    scale = float(np.abs(st["cost_volume"][0]).max())
+    np.testing.assert_allclose(L, st["cost_volume"][0], atol=COST_RTOL * scale, rtol=0)
+    np.testing.assert_allclose(R, st["cost_volume"][1], atol=COST_RTOL * scale, rtol=0)
+    L, R = pf.cost_volume_aggregation(li, ri, *st["cost_volume"], 0.02, 14, 2)
+    scale = float(np.abs(st["cbca1"][0]).max())
+    np.testing.assert_allclose(L, st["cbca1"][0], atol=CBCA_SEP_RTOL * scale, rtol=0)
+    L, R = pf.SGM_average(st["cbca1"][0].copy(), st["cbca1"][1].copy(), li, ri, 2.3, 55.9, 4, 8, 0.08, 1.5)
+    assert eq(L, st["sgm"][0]) and eq(R, st["sgm"][1])                      # bit-exact
+    L, R = pf.cost_volume_aggregation(li, ri, *st["sgm"], 0.02, 14, 16)
+    scale = float(np.abs(st["cbca2"][0]).max())
+    np.testing.assert_allclose(L, st["cbca2"][0], atol=16 * CBCA_SEP_RTOL * scale, rtol=0)
+    dl, dr = pf.disparity_prediction(*st["cbca2"])
+    assert eq(dl, st["wta"][0]) and eq(dr, st["wta"][1])                     # bit-identical indices
+    d = pf.interpolation(*st["wta"], D)
+    assert eq(d, st["interpolation"])
+    d = pf.subpixel_enhance(st["interpolation"], st["cbca2"][0])
+    assert eq(d, st["subpixel"])
+    d = pf.median_filter(st["subpixel"], 5, 5)
+    assert eq(d, st["median"])
+    d = pf.bilateral_filter(li, st["median"], 5, 5, 0, 6, 2)
+    np.testing.assert_allclose(d, st["bilateral"], rtol=2e-6, atol=1e-6)
+    # end to end (everything on the GPU, CUDA features): the maps agree except for rare near-tie flips
+    d2 = pkg.match_pair(li, ri, D, checkpoint=(ws, bs))
+    assert np.mean(np.abs(d2 - do) < 1e-3) > 0.97
+
+
+def test_config2_cost_volume_and_wta_vs_oracle(pf, oracle):
+    """BASELINE config 2: 512x512x128, cost volume + WTA only.  Cost volume within 1e-4 of the volume's scale; WTA of
+    the oracle's volume bit-identical; WTA of our own volume agrees except where the two smallest costs are closer than
+    the tolerance."""
+    H, W, D = 512, 512, 128
+    fl, fr = unit_features(7, H, W)
+    L, R = pf.compute_cost_volume(fl, fr, D)
+    Lo, Ro = oracle.compute_cost_volume(fl, fr, D)
+    scale = float(np.abs(Lo).max())
+    assert np.abs(L - Lo).max() <= COST_RTOL * scale and np.abs(R - Ro).max() <= COST_RTOL * scale
+    dl, dr = pf.disparity_prediction(Lo, Ro)
+    dlo, dro = oracle.disparity_prediction(Lo, Ro)
+    assert eq(dl, dlo) and eq(dr, dro)
+    dl2, _ = pf.disparity_prediction(L, R)
+    assert np.mean(dl2 == dlo) > 0.999
+
+
+def test_config3_full_size_properties(pkg):
+    """BASELINE config 3 size (1024x1024x192): size-independent properties of the whole pipeline object --
+    a pair shifted by a known disparity is recovered, and the run is deterministic (two runs are bit-identical)."""
+    import torch
+    H, W, D, shift = 1024, 1024, 192, 21
+    rng = np.random.default_rng(3)
+    base = rng.random((H, W + shift)).astype(np.float32)
+    k = np.ones(5, np.float32) / 5
+    base = np.apply_along_axis(lambda v: np.convolve(v, k, mode="same"), 1, base)
+    q = np.floor(base / base.max() * 255)
+    left, right = q[:, :W], q[:, shift:]
+    li = ((left - left.mean()) / left.std())[..., None].astype(np.float32)
+    ri = ((right - right.mean()) / right.std())[..., None].astype(np.float32)
+    m = pkg.StereoMatcher(H, W, D)
+    m.set_images(li, ri)
+    d1 = m.run().clone()
+    d2 = m.run().clone()
+    assert torch.equal(d1, d2)
+    inner = d1[16:-16, D:-16].cpu().numpy()
+    assert np.mean(np.abs(inner - shift) < 0.5) > 0.95, float(np.mean(np.abs(inner - shift) < 0.5))
+
+
 # ------------------------------------------------------------------------------------------ match.py drop-in
 def test_match_cli_writes_middlebury_outputs(pkg, tmp_path):
     """The match.py drop-in: list file + calib + images in, PFM / PGM / time file out (match.py:46-54, :182-184),
