@@ -23,33 +23,46 @@ __device__ __forceinline__ void cs_add(float4 &acc, const float4 v) {
 
 constexpr int CS_ITEMS = (CS_PH * CS_PW * CS_GC) / CS_THREADS;    // (pixel, granule) items per thread: 4
 
+__device__ __forceinline__ void cs_cp_async16(void *smem_dst, const void *gmem_src) {
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem_src));
+}
+
+// The centre cell and the two nearest neighbours of every item travel global -> shared with cp.async: bytes in
+// flight that cost no registers (these kernels are bound by memory-level parallelism, and most arms are 0 or 1 long,
+// so the common walk needs nothing else).  A thread reads back only its own slots: no barrier.
 __global__ void __launch_bounds__(CS_THREADS) k_cbca_rows(const float4 *__restrict__ in, float4 *__restrict__ hs,
                                                           const uchar4 *__restrict__ arms, int G, int H, int W) {
+    __shared__ float4 stage[3][CS_ITEMS][CS_THREADS];            // [centre, left, right]: 24 KB
     const int gi = threadIdx.x % CS_GC, g = blockIdx.z * CS_GC + gi;
     if (g >= G) return;
-    // all independent loads first (arms and centre cells of the thread's items): memory-level parallelism
-    size_t p[CS_ITEMS];
-    bool ok[CS_ITEMS];
+    int p[CS_ITEMS];
     uchar4 a[CS_ITEMS];
-    float4 c0[CS_ITEMS];
 #pragma unroll
     for (int s = 0; s < CS_ITEMS; s++) {
         const int pi = s * (CS_THREADS / CS_GC) + threadIdx.x / CS_GC;
         const int h = blockIdx.y * CS_PH + pi / CS_PW, w = blockIdx.x * CS_PW + pi % CS_PW;
-        ok[s] = h < H && w < W;
-        p[s] = ok[s] ? (size_t)h * W + w : 0;
-        a[s] = arms[p[s]];
-        c0[s] = in[p[s] * G + g];
+        p[s] = (h < H && w < W) ? h * W + w : -1;
+        if (p[s] >= 0) {
+            const float4 *c = in + (size_t)p[s] * G + g;
+            cs_cp_async16(&stage[0][s][threadIdx.x], c);
+            if (w > 0) cs_cp_async16(&stage[1][s][threadIdx.x], c - G);
+            if (w + 1 < W) cs_cp_async16(&stage[2][s][threadIdx.x], c + G);
+            a[s] = arms[p[s]];
+        }
     }
+    asm volatile("cp.async.wait_all;\n" ::: "memory");
 #pragma unroll
     for (int s = 0; s < CS_ITEMS; s++) {
-        if (!ok[s]) continue;
-        const float4 *c = in + p[s] * G + g;
+        if (p[s] < 0) continue;
+        const float4 *c = in + (size_t)p[s] * G + g;
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-        cs_add(acc, c0[s]);                                                      // w, w-1, .., w-left (pf:645-650)
-        for (int j = 1; j <= a[s].z; j++) cs_add(acc, c[-(ptrdiff_t)j * G]);
-        for (int j = 1; j <= a[s].w; j++) cs_add(acc, c[(ptrdiff_t)j * G]);      // w+1, .., w+right
-        hs[p[s] * G + g] = acc;
+        cs_add(acc, stage[0][s][threadIdx.x]);                                   // w, w-1, .., w-left (pf:645-650)
+        if (a[s].z >= 1) cs_add(acc, stage[1][s][threadIdx.x]);
+        for (int j = 2; j <= a[s].z; j++) cs_add(acc, c[-(ptrdiff_t)j * G]);
+        if (a[s].w >= 1) cs_add(acc, stage[2][s][threadIdx.x]);                  // w+1, .., w+right
+        for (int j = 2; j <= a[s].w; j++) cs_add(acc, c[(ptrdiff_t)j * G]);
+        hs[(size_t)p[s] * G + g] = acc;
     }
 }
 
