@@ -10,6 +10,8 @@
 #include "common.cuh"
 #include "cbca_tile.cuh"
 #include "cbca_stream.cuh"
+#include "cbca_march.cuh"
+#include <stdlib.h>
 
 namespace mccnn {
 
@@ -156,6 +158,53 @@ static int build_cbca_maps(CtMaps &maps, const float *vol, int G, int H, int W) 
     return MCCNN_OK;
 }
 
+// Tensor maps of one HWD volume for k_cbca_march: boxes {32 floats, WT | 2 | 13 pixels, 1 row}.
+static int build_cm_maps(CmMaps &maps, const float *vol, int G, int H, int W, int WT) {
+    EncodeTiledFn enc = encode_tiled_fn();
+    if (!enc) {
+        set_error("cbca: cuTensorMapEncodeTiled is not available from this driver");
+        return MCCNN_ERR_CUDA;
+    }
+    const cuuint64_t Dp = (cuuint64_t)G * 4;
+    const cuuint64_t gdim[3] = {Dp, (cuuint64_t)W, (cuuint64_t)H};
+    const cuuint64_t gstr[2] = {Dp * 4, (cuuint64_t)W * Dp * 4};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    CUtensorMap *m[3] = {&maps.centre, &maps.small, &maps.full};
+    const cuuint32_t px[3] = {(cuuint32_t)WT, (cuuint32_t)CM_HSMALL, (cuuint32_t)CM_ARM};
+    for (int i = 0; i < 3; i++) {
+        const cuuint32_t box[3] = {(cuuint32_t)(4 * CM_GT), px[i], 1};
+        CUresult r = enc(m[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void *)vol, gdim, gstr, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) {
+            set_error("cbca: cuTensorMapEncodeTiled failed (%d) for box %ux%u", (int)r, box[0], box[1]);
+            return MCCNN_ERR_CUDA;
+        }
+    }
+    return MCCNN_OK;
+}
+
+// The strip shapes k_cbca_march is built for: {strip width, TMA stages, CTAs per SM}.
+struct CmVariant { int wt, nst, per_sm; };
+static const CmVariant CM_VARIANTS[] = {{16, 3, 3}, {16, 6, 2}, {24, 3, 2}, {24, 4, 2}, {32, 5, 1}, {32, 3, 1}};
+static const int CM_NVARIANTS = (int)(sizeof(CM_VARIANTS) / sizeof(CM_VARIANTS[0]));
+static const int CM_DEFAULT_VARIANT = 0;
+
+template <int WT, int NST, int MINB>
+static int launch_march(const CmMaps &maps, float *dst, const uint8_t *arms, const int32_t *count, int G, int H, int W,
+                        int nW, int nG, int nseg, int hseg, cudaStream_t s) {
+    static bool attr_set = false;
+    const int smem = (int)sizeof(CmSmem<WT, NST>);
+    if (!attr_set) {
+        MCCNN_CUDA(cudaFuncSetAttribute(k_cbca_march<WT, NST, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        attr_set = true;
+    }
+    k_cbca_march<WT, NST, MINB><<<nW * nG * nseg, WT * CM_GT + 32, smem, s>>>(
+        maps, reinterpret_cast<float4 *>(dst), reinterpret_cast<const uchar4 *>(arms), count, G, H, W, nW, nG, hseg);
+    MCCNN_LAUNCHED("cbca_march");
+    return MCCNN_OK;
+}
+
 }  // namespace mccnn
 
 using namespace mccnn;
@@ -194,7 +243,8 @@ size_t mccnn_cbca_workspace_bytes(int H, int W) {
 
 int mccnn_cbca(const float *in, float *out, float *scratch, const uint8_t *arms, const int32_t *count, int D, int H,
                int W, int iters, int dist, int mode, void *workspace, void *stream) {
-    MCCNN_REQUIRE(mode == MCCNN_CBCA_SEPARABLE || mode == MCCNN_CBCA_EXACT || mode == MCCNN_CBCA_SEPARABLE_TILED,
+    MCCNN_REQUIRE(mode == MCCNN_CBCA_SEPARABLE || mode == MCCNN_CBCA_EXACT || mode == MCCNN_CBCA_SEPARABLE_TILED ||
+                      mode == MCCNN_CBCA_SEPARABLE_MARCH,
                   "cbca: unknown mode %d", mode);
     MCCNN_REQUIRE(dist >= 1 && dist <= 255, "cbca: distance_threshold %d outside [1, 255]", dist);
     MCCNN_REQUIRE(mode != MCCNN_CBCA_SEPARABLE_TILED || dist <= CT_MAXARM + 1,
@@ -202,13 +252,15 @@ int mccnn_cbca(const float *in, float *out, float *scratch, const uint8_t *arms,
     MCCNN_REQUIRE(in && out && arms && count && D >= 1 && H >= 1 && W >= 1 && iters >= 0, "cbca: bad arguments");
     MCCNN_REQUIRE(H <= 65535 && W <= 65535, "cbca: image too large");
     MCCNN_REQUIRE(in != out, "cbca: in and out must differ (the reference leaves its input untouched, pf:119)");
-    MCCNN_REQUIRE(iters < (mode == MCCNN_CBCA_SEPARABLE ? 1 : 2) || (scratch && scratch != in && scratch != out),
-                  "cbca: scratch volume required (separable: any round; other modes: iters >= 2)");
     MCCNN_REQUIRE(mode != MCCNN_CBCA_SEPARABLE_TILED || iters <= CBCA_MAX_ROUNDS, "cbca: at most %d rounds per call", CBCA_MAX_ROUNDS);
     MCCNN_REQUIRE(mode != MCCNN_CBCA_SEPARABLE_TILED || iters == 0 || workspace,
                   "cbca: separable mode needs a workspace of mccnn_cbca_workspace_bytes(H, W) bytes");
     cudaStream_t s = (cudaStream_t)stream;
     const int Dp = dpitch(D), G = Dp / 4;
+    // the marching kernel's boxes are 8 granules x up to 13 halo pixels: other shapes take the two streaming passes
+    if (mode == MCCNN_CBCA_SEPARABLE_MARCH && (dist > CM_ARM + 1 || G < CM_GT)) mode = MCCNN_CBCA_SEPARABLE;
+    MCCNN_REQUIRE(iters < (mode == MCCNN_CBCA_SEPARABLE ? 1 : 2) || (scratch && scratch != in && scratch != out),
+                  "cbca: scratch volume required (separable: any round; other modes: iters >= 2)");
     if (iters == 0) {
         MCCNN_CUDA(cudaMemcpyAsync(out, in, (size_t)H * W * Dp * sizeof(float), cudaMemcpyDeviceToDevice, s));
         return MCCNN_OK;
@@ -233,6 +285,60 @@ int mccnn_cbca(const float *in, float *out, float *scratch, const uint8_t *arms,
     buf[(iters - 1) & 1] = out;
     buf[iters & 1] = scratch;
     const float *src = in;
+    if (mode == MCCNN_CBCA_SEPARABLE_MARCH) {
+        static int num_sms_m = 0;
+        if (num_sms_m == 0) {
+            int dev = 0;
+            MCCNN_CUDA(cudaGetDevice(&dev));
+            MCCNN_CUDA(cudaDeviceGetAttribute(&num_sms_m, cudaDevAttrMultiProcessorCount, dev));
+        }
+        // MCCNN_CBCA_MARCH="variant[,row segments]" overrides the strip shape / segmentation (tuning and tests)
+        int variant = CM_DEFAULT_VARIANT, nseg = 0;
+        if (const char *e = getenv("MCCNN_CBCA_MARCH")) {
+            int v = -1, n = 0;
+            const int got = sscanf(e, "%d,%d", &v, &n);
+            if (got >= 1 && v >= 0 && v < CM_NVARIANTS) variant = v;
+            if (got >= 2 && n >= 1) nseg = n;
+        }
+        const CmVariant cv = CM_VARIANTS[variant];
+        const int nW = cdiv(W, cv.wt), nG = cdiv(G, CM_GT);
+        if (nseg == 0) {
+            // fewest (waves x rows marched per CTA): a segment re-forms the 13 row sums above and below it
+            const long long slots = (long long)num_sms_m * cv.per_sm;
+            long long best = -1;
+            for (int n = 1; n <= 16 && n <= H; n++) {
+                const long long units = (long long)nW * nG * n;
+                const long long cost = ((units + slots - 1) / slots) * (cdiv(H, n) + 2 * CM_ARM);
+                if (best < 0 || cost < best) { best = cost; nseg = n; }
+            }
+        }
+        if (nseg > H) nseg = H;
+        const int hseg = cdiv(H, nseg);
+        nseg = cdiv(H, hseg);
+        const float *vols[3] = {in, iters >= 2 ? buf[0] : nullptr, iters >= 3 ? buf[1] : nullptr};
+        CmMaps maps[3];
+        for (int v = 0; v < 3; v++)
+            if (vols[v]) {
+                int rc = build_cm_maps(maps[v], vols[v], G, H, W, cv.wt);
+                if (rc) return rc;
+            }
+        for (int it = 0; it < iters; it++) {
+            float *dst = buf[it & 1];
+            const CmMaps &m = maps[(src == in) ? 0 : (src == buf[0] ? 1 : 2)];
+            int rc;
+            switch (variant) {
+                case 0: rc = launch_march<16, 3, 3>(m, dst, arms, count, G, H, W, nW, nG, nseg, hseg, s); break;
+                case 1: rc = launch_march<16, 6, 2>(m, dst, arms, count, G, H, W, nW, nG, nseg, hseg, s); break;
+                case 2: rc = launch_march<24, 3, 2>(m, dst, arms, count, G, H, W, nW, nG, nseg, hseg, s); break;
+                case 3: rc = launch_march<24, 4, 2>(m, dst, arms, count, G, H, W, nW, nG, nseg, hseg, s); break;
+                case 4: rc = launch_march<32, 5, 1>(m, dst, arms, count, G, H, W, nW, nG, nseg, hseg, s); break;
+                default: rc = launch_march<32, 3, 1>(m, dst, arms, count, G, H, W, nW, nG, nseg, hseg, s); break;
+            }
+            if (rc) return rc;
+            src = dst;
+        }
+        return MCCNN_OK;
+    }
     if (mode == MCCNN_CBCA_EXACT) {
         dim3 grid(cdiv(W, CBCA_TW), cdiv(H, CBCA_TH));
         for (int it = 0; it < iters; it++) {

@@ -31,7 +31,7 @@ __all__ = ["compute_features", "compute_cost_volume", "cost_volume_aggregation",
 #       from the reference only by float32 re-association (~1e-7 relative);
 #   1 = "exact": the reference's flat running sum over the whole region (pf:157-161), bit-identical
 #       to the reference, <= 729 additions per cell.
-CBCA_SEPARABLE, CBCA_EXACT, CBCA_SEPARABLE_TILED = 0, 1, 2
+CBCA_SEPARABLE, CBCA_EXACT, CBCA_SEPARABLE_TILED, CBCA_SEPARABLE_MARCH = 0, 1, 2, 3
 CBCA_MODE = CBCA_SEPARABLE
 
 
@@ -265,7 +265,7 @@ def _cbca_one(hwd, D, arms, count, iters, dist, out=None, scratch=None, mode=Non
         mode = CBCA_MODE
     if mode == CBCA_SEPARABLE_TILED and int(dist) > 14:     # the tiled kernel's halo is sized for match.py's distance (14)
         mode = CBCA_SEPARABLE
-    if scratch is None and iters >= (1 if mode == CBCA_SEPARABLE else 2):
+    if scratch is None and iters >= 1:
         scratch = _empty_hwd(H, W, D)
     if workspace is None and mode == CBCA_SEPARABLE_TILED:
         workspace = cbca_workspace(H, W)

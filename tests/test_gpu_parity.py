@@ -210,6 +210,43 @@ def test_cbca_tiled_tma_mode_matches_streaming_mode_and_oracle(pf, oracle, monke
         np.testing.assert_allclose(Rt, Ro, atol=CBCA_SEP_RTOL * scale, rtol=0)
 
 
+def test_cbca_march_mode_matches_streaming_mode_and_oracle(pf, oracle, monkeypatch):
+    """MCCNN_CBCA_SEPARABLE_MARCH (one row-marching TMA kernel per round) forms the same sums in the same order
+    as the two streaming passes: identical results for every strip shape and row segmentation, and within the
+    re-association tolerance of the oracle.  Covers flat images (13-pixel arms: full halo boxes), ragged widths,
+    granule counts that are not a multiple of the strip's 8, images shorter than an arm, several row segments."""
+    cases = [(40, 90, 70, 4, 3), (33, 47, 192, 30, 2), (9, 29, 33, 1, 2), (50, 21, 40, 2, 3), (64, 64, 32, 1, 1),
+             (17, 200, 29, 3, 2), (70, 40, 100, 2, 2)]
+    for ci, (H, W, D, levels, iters) in enumerate(cases):
+        li, ri = synth_images(H * W + D, H, W, levels, 2)
+        rng = np.random.default_rng(D)
+        Lv = rng.standard_normal((D, H, W)).astype(np.float32) * 50
+        Rv = rng.standard_normal((D, H, W)).astype(np.float32) * 50
+        monkeypatch.setattr(pf, "CBCA_MODE", pf.CBCA_SEPARABLE)
+        monkeypatch.delenv("MCCNN_CBCA_MARCH", raising=False)
+        Ls, Rs = pf.cost_volume_aggregation(li, ri, Lv, Rv, 0.02, 14, iters)
+        monkeypatch.setattr(pf, "CBCA_MODE", pf.CBCA_SEPARABLE_MARCH)
+        Lt, Rt = pf.cost_volume_aggregation(li, ri, Lv, Rv, 0.02, 14, iters)
+        assert eq(Ls, Lt) and eq(Rs, Rt), (H, W, D)
+        for variant in range(6):
+            for nseg in ((1, 3) if ci % 2 else (2, 5)):
+                monkeypatch.setenv("MCCNN_CBCA_MARCH", "%d,%d" % (variant, nseg))
+                Lt, Rt = pf.cost_volume_aggregation(li, ri, Lv, Rv, 0.02, 14, iters)
+                assert eq(Ls, Lt) and eq(Rs, Rt), (H, W, D, variant, nseg)
+        monkeypatch.delenv("MCCNN_CBCA_MARCH", raising=False)
+        Lo, Ro = oracle.cost_volume_aggregation(li, ri, Lv, Rv, 0.02, 14, iters)
+        scale = float(np.abs(Lo).max())
+        np.testing.assert_allclose(Lt, Lo, atol=CBCA_SEP_RTOL * scale, rtol=0)
+        np.testing.assert_allclose(Rt, Ro, atol=CBCA_SEP_RTOL * scale, rtol=0)
+    # shapes the marching kernel is not built for fall back to the streaming passes (still correct)
+    Li = rng.integers(0, 64, (12, 30, 44)).astype(np.float32)
+    li, ri = synth_images(5, 30, 44, 3, 1)
+    for dist in (14, 20):
+        Lg, _ = pf.cost_volume_aggregation(li, ri, Li, Li, 0.02, dist, 2)
+        Lo, _ = oracle.cost_volume_aggregation(li, ri, Li, Li, 0.02, dist, 2)
+        np.testing.assert_allclose(Lg, Lo, atol=CBCA_SEP_RTOL * 64, rtol=0)
+
+
 def test_cbca_plane_constant_is_fixed_point(pf):
     """Property (any size): a volume that is constant per disparity plane with small-integer values is a
     fixed point of region averaging (exact sums, exact division)."""
