@@ -136,6 +136,44 @@ int mccnn_median(const float *in, float *out, int H, int W, int fh, int fw, void
 int mccnn_bilateral(const float *img, const float *in, float *out, const float *table,
                     int H, int W, int fh, int fw, float blur_threshold, void *stream);
 
+/* ---- One big pair partitioned over GPUs by disparity slab (the reference has no such mode: its
+ * only parallelism is disjoint pair windows, match.py:26-28).  A slab [d_base, d_base + d_count) of a volume is its
+ * own HWD volume of d_count disparities; d_base is a multiple of 4.  Cost volume, CBCA and WTA are independent
+ * per disparity plane and run on slabs; SGM needs every disparity of a pixel and runs on row slabs (horizontal
+ * passes) and column slabs (vertical passes) after a re-partition (mccnn_copy3d + all-to-all). */
+
+/* a3 restricted to disparities [d_base, d_base + d_count) of an ndisp = D problem (pf:78-113). */
+int mccnn_cost_volume_slab(const float *fl, const float *fr, float *L, float *R,
+                           int H, int W, int C, int D, int d_base, int d_count, void *stream);
+
+/* a6/a7: two of the four chained passes (pf:194-208).  which = 0: (0,1) then (0,-1) on a ROW slab -- volumes
+ * [H][W][Dp] and images hold the slab's H rows, w_base = 0, w_count = W.  which = 1: (-1,0) then (1,0) on a COLUMN
+ * slab -- volumes [H][w_count][Dp] hold image columns [w_base, w_base + w_count), images are whole [H][W].
+ * flags_scratch: mccnn_sgm_scratch_bytes(H, W, D). */
+int mccnn_sgm_passes_slab(float *vol_left, float *vol_right, const float *img_left, const float *img_right,
+                          void *flags_scratch, int D, int H, int W, int w_base, int w_count, int which,
+                          double sgm_P1, double sgm_P2, double sgm_Q1, double sgm_Q2, double sgm_D,
+                          double sgm_V, void *stream);
+
+/* a8 on a slab of D disparities starting at d_base: disp = the pair's disparity of the slab's first minimum,
+ * minval = its cost.  mccnn_wta_combine takes the all-gathered arrays (slab s at element s * slab_stride) and keeps, per pixel, the
+ * first strict minimum in slab order (the lowest disparity wins ties, pf:247-252). */
+int mccnn_wta_slab(const float *vol, float *disp, float *minval, int D, int H, int W, int d_base, void *stream);
+int mccnn_wta_combine(const float *minvals, const float *disps, float *out, int nslabs, long long slab_stride,
+                      int H, int W, void *stream);
+
+/* a10 on a slab: triple [3][H][W] = (C[d-1], C[d], C[d+1]) of pf:392-394 where this slab owns the cell, else 0
+ * (a sum over the slabs restores the cells exactly); mccnn_subpixel_triple applies pf:395-398 to the summed triple. */
+int mccnn_subpixel_gather(const float *disp, const float *vol, float *triple, int D, int H, int W, int d_base,
+                          int ndisp, void *stream);
+int mccnn_subpixel_triple(const float *disp, const float *triple, float *out, int ndisp, int H, int W, void *stream);
+
+/* Strided block copy [n0][n1][n2_granules x 16 bytes]; strides in 16-byte granules.  Packs / unpacks the blocks a
+ * re-partition exchanges (rows <-> columns <-> disparity slabs of an HWD volume). */
+int mccnn_copy3d(const float *src, float *dst, long long n0, long long n1, int n2_granules,
+                 long long src_stride0, long long src_stride1, long long dst_stride0, long long dst_stride1,
+                 void *stream);
+
 #ifdef __cplusplus
 }
 #endif

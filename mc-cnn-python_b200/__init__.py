@@ -11,3 +11,5 @@ from . import model                     # noqa: F401
 from . import pipeline                  # noqa: F401
 from .model import NET                  # noqa: F401
 from .pipeline import StereoMatcher, match_pair, shard_window, DEFAULTS   # noqa: F401
+from . import slab                      # noqa: F401
+from .slab import SlabPlan, SlabRank, SlabMatcher, LocalComm, DistComm, run_slabs   # noqa: F401

@@ -37,6 +37,14 @@ SIGNATURES = {
     "mccnn_subpixel": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),
     "mccnn_median": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
     "mccnn_bilateral": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _vp]),
+    "mccnn_cost_volume_slab": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
+    "mccnn_sgm_passes_slab": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _d, _d, _d, _d, _d, _d, _vp]),
+    "mccnn_wta_slab": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "mccnn_wta_combine": (_i, [_vp, _vp, _vp, _i, _c.c_longlong, _i, _i, _vp]),
+    "mccnn_subpixel_gather": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "mccnn_subpixel_triple": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),
+    "mccnn_copy3d": (_i, [_vp, _vp, _c.c_longlong, _c.c_longlong, _i, _c.c_longlong, _c.c_longlong, _c.c_longlong,
+                          _c.c_longlong, _vp]),
 }
 
 _lib = None

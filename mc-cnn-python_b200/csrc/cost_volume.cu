@@ -84,7 +84,10 @@ __device__ __forceinline__ void cv_store_quarter(float *__restrict__ vol, unsign
 
 __global__ void __launch_bounds__(CV_THREADS, 1)
 k_cost_volume_tc(const __grid_constant__ CvMaps maps, float *__restrict__ L, float *__restrict__ R, int H, int W, int D,
-                 int Dp, int nwt, int nchunks, int ntiles) {
+                 int Dp, int nwt, int nchunks, int ntiles, int dbase) {
+    // Disparity slab [dbase, dbase + D): the right pixel matched at local disparity d is x = w - dbase - d, so the
+    // right chunks are fetched (and the R cells stored) dbase pixels to the left of where the local band sits;
+    // chunks left of the image are zero-filled by the TMA unit and land in the triangle k_cost_fill overwrites.
     extern __shared__ __align__(1024) unsigned char cv_raw[];
     CvSmem &sm = *reinterpret_cast<CvSmem *>(cv_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -121,8 +124,8 @@ k_cost_volume_tc(const __grid_constant__ CvMaps maps, float *__restrict__ L, flo
                 const int x0c = w0 + CV_BM - CV_BN * nchunks + CV_BN * c;
                 unsigned char *dst = sm.b_hi[g & 1];
                 tc_mbar_expect_tx(&sm.bar_tma_b[g & 1], CV_TILE_BYTES);
-                tc_tma_load_3d(dst, &maps.fr, 0, x0c, h, &sm.bar_tma_b[g & 1]);
-                tc_tma_load_3d(dst + CV_KB_BYTES, &maps.fr, 32, x0c, h, &sm.bar_tma_b[g & 1]);
+                tc_tma_load_3d(dst, &maps.fr, 0, x0c - dbase, h, &sm.bar_tma_b[g & 1]);
+                tc_tma_load_3d(dst + CV_KB_BYTES, &maps.fr, 32, x0c - dbase, h, &sm.bar_tma_b[g & 1]);
             };
             auto issue_a = [&](int tile) {
                 const int h = tile / nwt, w0 = (tile - h * nwt) * CV_BM;
@@ -211,7 +214,7 @@ k_cost_volume_tc(const __grid_constant__ CvMaps maps, float *__restrict__ L, flo
                 const unsigned t_s = tmem_base + ((unsigned)(32 * q) << 16) + buf * (2 * CV_BN), t_t = t_s + CV_BN;
                 if (!does_l) {
                     // R[h][x][d]: lanes are left pixels w = w0 + 32q + lane, columns right pixels x = x0c + n, d = w - x
-                    cv_store_quarter<+1>(R, t_s, rowbase, x0c, w0 + 32 * q - x0c, w0 + 32 * q + lane < W, W, D, Dp);
+                    cv_store_quarter<+1>(R, t_s, rowbase, x0c - dbase, w0 + 32 * q - x0c, w0 + 32 * q + lane < W, W, D, Dp);
                 } else {
                     // L[h][w][d]: lanes are right pixels x = x0c + 32q + lane, columns left pixels w = w0 + n, d = w - x
                     cv_store_quarter<-1>(L, t_t, rowbase, w0, w0 - x0c - 32 * q, true, W, D, Dp);
@@ -230,31 +233,32 @@ k_cost_volume_tc(const __grid_constant__ CvMaps maps, float *__restrict__ L, flo
 // Invalid triangles (pf:94-95 for L, pf:105-106 for R), in the already negated domain (negation
 // commutes exactly with the mean).  One warp per (row, 32 disparities); lanes over d so that the
 // cells written at each step are contiguous; each lane slides a 3-value window along w.
-__global__ void k_cost_fill(float *__restrict__ L, float *__restrict__ R, int H, int W, int D, int Dp) {
+__global__ void k_cost_fill(float *__restrict__ L, float *__restrict__ R, int H, int W, int D, int Dp, int dbase) {
     const int lane = threadIdx.x & 31;
     const int h = blockIdx.y;
     const int d0 = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 32;
     if (d0 >= D) return;
-    const int d = d0 + lane;
-    const bool live = d < D && d >= 1;
-    const int dmax = min(d0 + 31, D - 1);
+    const int dl = d0 + lane;                                   // disparity inside the slab (the volume's index)
+    const int d = dbase + dl;                                   // disparity (the triangle's extent)
+    const bool live = dl < D && d >= 1;
+    const int dmax = dbase + min(d0 + 31, D - 1);
     float *Lrow = L + (size_t)h * W * Dp;
     float *Rrow = R + (size_t)h * W * Dp;
-    // the three valid cells each recurrence starts from (W >= D + 2 keeps them inside the row): all loads first
+    // the three valid cells each recurrence starts from (W >= ndisp + 2 keeps them inside the row): all loads first
     float l1 = 0.f, l2 = 0.f, l3 = 0.f, r1 = 0.f, r2 = 0.f, r3 = 0.f;
     if (live) {
-        l1 = Lrow[(size_t)d * Dp + d];                          // columns d, d+1, d+2
-        l2 = Lrow[(size_t)(d + 1) * Dp + d];
-        l3 = Lrow[(size_t)(d + 2) * Dp + d];
-        r1 = Rrow[(size_t)(W - d - 1) * Dp + d];                // columns W-d-1, W-d-2, W-d-3
-        r2 = Rrow[(size_t)(W - d - 2) * Dp + d];
-        r3 = Rrow[(size_t)(W - d - 3) * Dp + d];
+        l1 = Lrow[(size_t)d * Dp + dl];                         // columns d, d+1, d+2
+        l2 = Lrow[(size_t)(d + 1) * Dp + dl];
+        l3 = Lrow[(size_t)(d + 2) * Dp + dl];
+        r1 = Rrow[(size_t)(W - d - 1) * Dp + dl];               // columns W-d-1, W-d-2, W-d-3
+        r2 = Rrow[(size_t)(W - d - 2) * Dp + dl];
+        r3 = Rrow[(size_t)(W - d - 3) * Dp + dl];
     }
     // L: columns d-1 .. 0, right to left (pf:94-95); lanes over d so that each step writes a contiguous run
     for (int c = dmax - 1; c >= 0; c--) {
         if (live && c <= d - 1) {
             const float v = ((l1 + l2) + l3) / 3.0f;
-            Lrow[(size_t)c * Dp + d] = v;
+            Lrow[(size_t)c * Dp + dl] = v;
             l3 = l2; l2 = l1; l1 = v;
         }
     }
@@ -262,7 +266,7 @@ __global__ void k_cost_fill(float *__restrict__ L, float *__restrict__ R, int H,
     for (int c = W - dmax; c < W; c++) {
         if (live && c >= W - d) {
             const float v = ((r3 + r2) + r1) / 3.0f;
-            Rrow[(size_t)c * Dp + d] = v;
+            Rrow[(size_t)c * Dp + dl] = v;
             r3 = r2; r2 = r1; r1 = v;
         }
     }
@@ -274,10 +278,12 @@ using namespace mccnn;
 
 extern "C" {
 
-int mccnn_cost_volume(const float *fl, const float *fr, float *L, float *R, int H, int W, int C, int D, void *stream) {
+static int cost_volume_slab(const float *fl, const float *fr, float *L, float *R, int H, int W, int C, int Dtot, int dbase,
+                            int D, void *stream) {
     MCCNN_REQUIRE(fl && fr && L && R, "cost_volume: null pointer");
     MCCNN_REQUIRE(C == CV_C, "cost_volume: %d feature channels unsupported (the network emits 64, model.py:38)", C);
-    MCCNN_REQUIRE(H >= 1 && D >= 1 && W >= D + 2, "cost_volume: need W >= ndisp + 2 (pf:94-95), got W=%d ndisp=%d", W, D);
+    MCCNN_REQUIRE(H >= 1 && Dtot >= 1 && W >= Dtot + 2, "cost_volume: need W >= ndisp + 2 (pf:94-95), got W=%d ndisp=%d", W, Dtot);
+    MCCNN_REQUIRE(dbase >= 0 && D >= 1 && dbase + D <= Dtot, "cost_volume: slab [%d, %d) outside [0, %d)", dbase, dbase + D, Dtot);
     MCCNN_REQUIRE(D <= 512, "cost_volume: ndisp %d too large (max 512)", D);
     MCCNN_REQUIRE(((uintptr_t)fl & 15) == 0 && ((uintptr_t)fr & 15) == 0, "cost_volume: features must be 16-byte aligned");
     cudaStream_t s = (cudaStream_t)stream;
@@ -302,14 +308,23 @@ int mccnn_cost_volume(const float *fl, const float *fr, float *L, float *R, int 
     const long long ntiles = (long long)nwt * H;
     MCCNN_REQUIRE(ntiles < (1ll << 31), "cost_volume: image too large");
     const int grid = ntiles < num_sms ? (int)ntiles : num_sms;
-    k_cost_volume_tc<<<grid, CV_THREADS, sizeof(CvSmem), s>>>(maps, L, R, H, W, D, Dp, nwt, nchunks, (int)ntiles);
+    k_cost_volume_tc<<<grid, CV_THREADS, sizeof(CvSmem), s>>>(maps, L, R, H, W, D, Dp, nwt, nchunks, (int)ntiles, dbase);
     MCCNN_LAUNCHED("cost_volume_tc");
-    if (D > 1) {
+    if (dbase + D > 1) {
         dim3 fgrid(cdiv(cdiv(D, 32), 4), H);
-        k_cost_fill<<<fgrid, 128, 0, s>>>(L, R, H, W, D, Dp);
+        k_cost_fill<<<fgrid, 128, 0, s>>>(L, R, H, W, D, Dp, dbase);
         MCCNN_LAUNCHED("cost_fill");
     }
     return MCCNN_OK;
+}
+
+int mccnn_cost_volume(const float *fl, const float *fr, float *L, float *R, int H, int W, int C, int D, void *stream) {
+    return cost_volume_slab(fl, fr, L, R, H, W, C, D, 0, D, stream);
+}
+
+int mccnn_cost_volume_slab(const float *fl, const float *fr, float *L, float *R, int H, int W, int C, int D, int d_base,
+                           int d_count, void *stream) {
+    return cost_volume_slab(fl, fr, L, R, H, W, C, D, d_base, d_count, stream);
 }
 
 }  // extern "C"

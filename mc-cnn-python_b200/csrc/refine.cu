@@ -13,7 +13,7 @@ namespace mccnn {
 // ------------------------------------------------------------------------------------------
 template <int GS, int NL>
 __global__ void __launch_bounds__(256) k_wta(const float *__restrict__ vol, float *__restrict__ disp,
-                                             int D, int Dp, long long P) {
+                                             float *__restrict__ minval, int dbase, int D, int Dp, long long P) {
     const int lane_in_group = threadIdx.x % GS;
     long long p = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / GS;
     const bool live = p < P;
@@ -53,7 +53,10 @@ __global__ void __launch_bounds__(256) k_wta(const float *__restrict__ vol, floa
         bool take = (od >= 0) && (bd < 0 || ov < best || (ov == best && od < bd));
         if (take) { best = ov; bd = od; }
     }
-    if (live && lane_in_group == 0) disp[p] = (float)bd;
+    if (live && lane_in_group == 0) {
+        disp[p] = (float)(dbase + bd);                      // (a disparity slab reports the pair's disparity)
+        if (minval) minval[p] = best;
+    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -137,6 +140,51 @@ __global__ void k_subpixel(const float *__restrict__ disp, const float *__restri
     float num = Cp - Cm;
     float den = 2.0f * ((Cp - 2.0f * C) + Cm);
     out[p] = d - num / den;                                        // pf:396 (IEEE division; inf/NaN propagate)
+}
+
+// The same on a disparity-slab partition: triple [3][P] = (C[d-1], C[d], C[d+1]) restricted to this slab.
+__global__ void k_subpixel_gather(const float *__restrict__ disp, const float *__restrict__ vol, float *__restrict__ triple,
+                                  int D, int Dp, int dbase, int ndisp, long long P) {
+    long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= P) return;
+    const float d = disp[p];
+    int im = (int)(d - 1.0f), ip = (int)(d + 1.0f), ic = (int)d;
+    float Cm = 0.f, C = 0.f, Cp = 0.f;
+    if (!(im < 0 || ip >= ndisp || !(d == d))) {
+        ic = ic < 0 ? 0 : (ic >= ndisp ? ndisp - 1 : ic);
+        const float *row = vol + p * Dp - dbase;
+        if (im >= dbase && im < dbase + D) Cm = row[im];
+        if (ic >= dbase && ic < dbase + D) C = row[ic];
+        if (ip >= dbase && ip < dbase + D) Cp = row[ip];
+    }
+    triple[p] = Cm;
+    triple[P + p] = C;
+    triple[2 * P + p] = Cp;
+}
+
+__global__ void k_subpixel_triple(const float *__restrict__ disp, const float *__restrict__ triple, float *__restrict__ out,
+                                  int ndisp, long long P) {
+    long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= P) return;
+    const float d = disp[p];
+    const int im = (int)(d - 1.0f), ip = (int)(d + 1.0f);
+    if (im < 0 || ip >= ndisp || !(d == d)) { out[p] = d; return; }
+    const float Cm = triple[p], C = triple[P + p], Cp = triple[2 * P + p];
+    const float num = Cp - Cm;
+    const float den = 2.0f * ((Cp - 2.0f * C) + Cm);
+    out[p] = d - num / den;                                        // pf:396
+}
+
+__global__ void k_wta_combine(const float *__restrict__ minvals, const float *__restrict__ disps, float *__restrict__ out,
+                              int nslabs, long long stride, long long P) {
+    long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= P) return;
+    float best = CUDART_INF_F, bd = -1.0f;
+    for (int s = 0; s < nslabs; s++) {
+        const float v = minvals[(size_t)s * stride + p];
+        if (v < best) { best = v; bd = disps[(size_t)s * stride + p]; }
+    }
+    out[p] = bd;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -248,13 +296,13 @@ using namespace mccnn;
 
 extern "C" {
 
-int mccnn_wta(const float *vol, float *disp, int D, int H, int W, void *stream) {
-    MCCNN_REQUIRE(vol && disp && D >= 1 && H >= 1 && W >= 1, "wta: bad arguments");
+static int wta_launch(const float *vol, float *disp, float *minval, int dbase, int D, int H, int W, void *stream) {
+    MCCNN_REQUIRE(vol && disp && D >= 1 && H >= 1 && W >= 1 && dbase >= 0, "wta: bad arguments");
     long long P = (long long)H * W;
     int Dp = dpitch(D), G = Dp / 4;
     cudaStream_t s = (cudaStream_t)stream;
     const int T = 256;
-#define WTA_CASE(GS, NL) k_wta<GS, NL><<<cdiv(P * GS, T), T, 0, s>>>(vol, disp, D, Dp, P)
+#define WTA_CASE(GS, NL) k_wta<GS, NL><<<cdiv(P * GS, T), T, 0, s>>>(vol, disp, minval, dbase, D, Dp, P)
     if (G > 64) WTA_CASE(32, 4);
     else if (G >= 12) WTA_CASE(16, 4);
     else if (G >= 6) WTA_CASE(8, 2);
@@ -262,6 +310,46 @@ int mccnn_wta(const float *vol, float *disp, int D, int H, int W, void *stream) 
     else WTA_CASE(2, 1);
 #undef WTA_CASE
     MCCNN_LAUNCHED("wta");
+    return MCCNN_OK;
+}
+
+int mccnn_wta(const float *vol, float *disp, int D, int H, int W, void *stream) {
+    return wta_launch(vol, disp, nullptr, 0, D, H, W, stream);
+}
+
+/* Disparity slab [d_base, d_base + D) of one big pair: the slab's first minimum and its cost. */
+int mccnn_wta_slab(const float *vol, float *disp, float *minval, int D, int H, int W, int d_base, void *stream) {
+    MCCNN_REQUIRE(minval, "wta_slab: null pointer");
+    return wta_launch(vol, disp, minval, d_base, D, H, W, stream);
+}
+
+/* First minimum over the slabs, in slab order (strict <: the lowest disparity wins ties, pf:247-252). */
+int mccnn_wta_combine(const float *minvals, const float *disps, float *out, int nslabs, long long slab_stride, int H,
+                      int W, void *stream) {
+    long long P = (long long)H * W;
+    MCCNN_REQUIRE(minvals && disps && out && nslabs >= 1 && H >= 1 && W >= 1 && slab_stride >= P, "wta_combine: bad arguments");
+    k_wta_combine<<<cdiv(P, 256), 256, 0, (cudaStream_t)stream>>>(minvals, disps, out, nslabs, slab_stride, P);
+    MCCNN_LAUNCHED("wta_combine");
+    return MCCNN_OK;
+}
+
+/* Sub-pixel on a disparity-slab partition: every slab contributes the cells of {d-1, d, d+1} it owns (0 for the
+ * others, so that a sum over the slabs restores the three cells exactly), then the formula of pf:381-400. */
+int mccnn_subpixel_gather(const float *disp, const float *vol, float *triple, int D, int H, int W, int d_base,
+                          int ndisp, void *stream) {
+    MCCNN_REQUIRE(disp && vol && triple && D >= 1 && H >= 1 && W >= 1 && d_base >= 0 && d_base + D <= ndisp,
+                  "subpixel_gather: bad arguments");
+    long long P = (long long)H * W;
+    k_subpixel_gather<<<cdiv(P, 256), 256, 0, (cudaStream_t)stream>>>(disp, vol, triple, D, dpitch(D), d_base, ndisp, P);
+    MCCNN_LAUNCHED("subpixel_gather");
+    return MCCNN_OK;
+}
+
+int mccnn_subpixel_triple(const float *disp, const float *triple, float *out, int ndisp, int H, int W, void *stream) {
+    MCCNN_REQUIRE(disp && triple && out && ndisp >= 1 && H >= 1 && W >= 1, "subpixel_triple: bad arguments");
+    long long P = (long long)H * W;
+    k_subpixel_triple<<<cdiv(P, 256), 256, 0, (cudaStream_t)stream>>>(disp, triple, out, ndisp, P);
+    MCCNN_LAUNCHED("subpixel_triple");
     return MCCNN_OK;
 }
 

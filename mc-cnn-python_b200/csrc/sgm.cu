@@ -27,7 +27,8 @@ struct SgmJob {
 
 struct SgmParams {
     SgmJob job[2];
-    int D, G, NLg, H, W, WR, PADW;
+    int D, G, NLg, H, W, WR, PADW;   // W = width of the volume (and of the images unless wbase/flag geometry say otherwise)
+    int wbase;                       // image column of the volume's column 0 (column slabs of one big pair)
     int rh, rw;
     float P1, P2, P1q1, P2q1, P1q2, P2q2;
 };
@@ -136,7 +137,7 @@ __global__ void __launch_bounds__(32, 16) k_sgm_pass(const __grid_constant__ Sgm
     // that the loads are never waited for at issue.
     struct FlagWords { uint32_t lo[JP], hi[JP], own; };
     auto flag_pos = [&](int t, int &pos1) {
-        const int wb = w0 + t * dw + woff;
+        const int wb = prm.wbase + w0 + t * dw + woff;
         pos1 = prm.PADW * 32 + wb;
         return h0 + t * dh + hoff;
     };
@@ -282,7 +283,7 @@ static int check_dir(int rh, int rw) {
 
 static void fill_params(SgmParams &prm, int D, int H, int W, int rh, int rw, double P1, double P2, double Q1, double Q2) {
     SgmGeom gm = sgm_geom(H, W, D);
-    prm.D = D; prm.G = dpitch(D) / 4; prm.H = H; prm.W = W; prm.WR = gm.WR; prm.PADW = gm.PADW;
+    prm.D = D; prm.G = dpitch(D) / 4; prm.H = H; prm.W = W; prm.WR = gm.WR; prm.PADW = gm.PADW; prm.wbase = 0;
     prm.NLg = cdiv(prm.G, cdiv(prm.G, 32));
     prm.rh = rh; prm.rw = rw;
     // float32 rounding exactly as pf:504-505 (P*ones(float32)) and pf:538-541 (float32 array / scalar)
@@ -349,6 +350,41 @@ int mccnn_sgm_average_pair(float *vol_left, float *vol_right, const float *img_l
         SgmParams prm;
         // vertical passes use P1/V formed in float64 by the caller (pf:204), then rounded to float32
         fill_params(prm, D, H, W, rh, rw, rh == 0 ? P1 : P1 / V, P2, Q1, Q2);
+        int n = 0;
+        if (vol_left) fill_job(prm.job[n++], vol_left, maps, H, W, D, rh, 1);
+        if (vol_right) fill_job(prm.job[n++], vol_right, maps, H, W, D, rh, 0);
+        if (n == 1) prm.job[1] = prm.job[0];
+        rc = launch_pass(prm, n, s);
+        if (rc) return rc;
+    }
+    return MCCNN_OK;
+}
+
+// Two of the four chained passes on a slab of one big pair: which = 0 runs (0,1) then (0,-1) on a
+// ROW slab (volumes [h_count][W][Dp], images passed from their row h_base: rows are independent for horizontal
+// passes), which = 1 runs (-1,0) then (1,0) on a COLUMN slab (volumes [H][w_count][Dp] holding image columns
+// [w_base, w_base + w_count), full images: the penalty tests look up the other image at column w -/+ d).
+int mccnn_sgm_passes_slab(float *vol_left, float *vol_right, const float *img_left, const float *img_right,
+                          void *flags_scratch, int D, int H, int W, int w_base, int w_count, int which, double P1,
+                          double P2, double Q1, double Q2, double tauD, double V, void *stream) {
+    MCCNN_REQUIRE((vol_left || vol_right) && img_left && img_right && flags_scratch, "sgm_passes_slab: null pointer");
+    MCCNN_REQUIRE(D >= 2 && H >= 1 && W >= 1, "sgm_passes_slab: need ndisp >= 2, got D=%d H=%d W=%d", D, H, W);
+    MCCNN_REQUIRE(w_base >= 0 && w_count >= 1 && w_base + w_count <= W, "sgm_passes_slab: columns [%d, %d) outside the image",
+                  w_base, w_base + w_count);
+    MCCNN_REQUIRE(which == 0 || which == 1, "sgm_passes_slab: which must be 0 (horizontal) or 1 (vertical)");
+    MCCNN_REQUIRE(which == 1 || (w_base == 0 && w_count == W), "sgm_passes_slab: horizontal passes need whole rows");
+    MCCNN_REQUIRE(tauD > 0.0 && V != 0.0, "sgm_passes_slab: sgm_D must be > 0 and sgm_V non-zero");
+    cudaStream_t s = (cudaStream_t)stream;
+    uint32_t *maps = (uint32_t *)flags_scratch;
+    int rc = build_flags(img_left, img_right, maps, H, W, D, (float)tauD, s);
+    if (rc) return rc;
+    const int dirs[2][2][2] = {{{0, 1}, {0, -1}}, {{-1, 0}, {1, 0}}};      // pf:195, :198 | pf:203, :207
+    for (int i = 0; i < 2; i++) {
+        const int rh = dirs[which][i][0], rw = dirs[which][i][1];
+        SgmParams prm;
+        fill_params(prm, D, H, W, rh, rw, rh == 0 ? P1 : P1 / V, P2, Q1, Q2);     // flag geometry of the full image
+        prm.W = w_count;
+        prm.wbase = w_base;
         int n = 0;
         if (vol_left) fill_job(prm.job[n++], vol_left, maps, H, W, D, rh, 1);
         if (vol_right) fill_job(prm.job[n++], vol_right, maps, H, W, D, rh, 0);

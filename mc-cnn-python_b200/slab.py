@@ -1,0 +1,381 @@
+"""One big stereo pair across several GPUs: the disparity-slab partition of SURVEY.md 8(e) (BASELINE config C5).
+
+The reference has no such mode (its only parallelism is disjoint pair windows, match.py:26-28); the stage order
+and every per-cell result are those of match.py:131-175, only *where* a cell is computed changes:
+
+  features              replicated (0.6 MB of weights, the pair's two images)
+  cost volume, CBCA     rank g owns disparities [d_base_g, d_base_g + d_count_g): independent per disparity plane
+                        (pf:94-95 runs along w inside one d; cross regions ignore d)
+  SGM                   needs all disparities of a pixel (pf:549-566): the volumes are re-partitioned
+                        d-slabs -> row slabs (the two horizontal passes) -> column slabs (the two vertical passes)
+                        -> d-slabs, three exchanges per volume (grouped send/recv = all-to-all over NVLink),
+                        blocks packed / unpacked by mccnn_copy3d
+  WTA                   per-slab first minimum + its cost, all-gather, first strict minimum in slab order
+  sub-pixel             the three cells around d* may sit in a neighbour slab (the slab seam): every slab contributes
+                        the cells it owns, summed over the ranks (exact: the other terms are 0)
+  LR check, median, bilateral   O(H*W), replicated.
+
+``SlabPlan`` is pure index arithmetic (tested on CPU), ``SlabRank`` owns one rank's device buffers and issues its
+C-ABI calls, ``run_slabs`` drives one or more ranks through the phases with a communicator: ``DistComm``
+(torch.distributed: NCCL on GPUs, gloo in the CPU tests) or ``LocalComm`` (all ranks inside one process on one
+GPU: used to check the partition against the single-GPU pipeline bit for bit).
+"""
+import ctypes
+
+import numpy as np
+
+try:
+    from . import _ffi
+    from . import process_functional as _pf
+    from .pipeline import DEFAULTS
+except ImportError:
+    import _ffi
+    import process_functional as _pf
+    from pipeline import DEFAULTS
+
+
+def _split(n, parts):
+    """Balanced contiguous split of range(n): list of (lo, hi)."""
+    base, extra = divmod(int(n), int(parts))
+    out, lo = [], 0
+    for r in range(parts):
+        hi = lo + base + (1 if r < extra else 0)
+        out.append((lo, hi))
+        lo = hi
+    return out
+
+
+class SlabPlan(object):
+    """Who owns what.  Disparities are split in whole 16-byte granules (4 disparities) so that a slab is itself
+    an HWD volume; rows and columns are split evenly."""
+
+    def __init__(self, H, W, D, world):
+        self.H, self.W, self.D, self.world = int(H), int(W), int(D), int(world)
+        self.G = _ffi.dpitch(self.D) // 4
+        assert self.world >= 1 and self.G >= self.world and self.H >= self.world and self.W >= self.world, \
+            "need at least one disparity granule, one row and one column per rank"
+        self.granules = _split(self.G, self.world)
+        self.rows = _split(self.H, self.world)
+        self.cols = _split(self.W, self.world)
+
+    def d_base(self, r):
+        return 4 * self.granules[r][0]
+
+    def d_count(self, r):
+        """Disparities of slab r (the last slab may end inside its last granule)."""
+        return min(self.D, 4 * self.granules[r][1]) - self.d_base(r)
+
+    def g_count(self, r):
+        return self.granules[r][1] - self.granules[r][0]
+
+    def h_count(self, r):
+        return self.rows[r][1] - self.rows[r][0]
+
+    def w_count(self, r):
+        return self.cols[r][1] - self.cols[r][0]
+
+    def owner_of_disparity(self, d):
+        for r in range(self.world):
+            if self.d_base(r) <= d < self.d_base(r) + self.d_count(r):
+                return r
+        raise ValueError(d)
+
+
+# ---------------------------------------------------------------------------------------------- communicators
+class LocalComm(object):
+    """All ranks live in this process (one GPU): an exchange is a set of device copies."""
+
+    def __init__(self, world):
+        self.world = int(world)
+
+    def exchange(self, sends, recvs):
+        """sends[i][j] = block rank i sends to rank j; recvs[j][i] = where rank j receives it."""
+        for i in range(self.world):
+            for j in range(self.world):
+                recvs[j][i].copy_(sends[i][j])
+
+    def all_gather(self, parts):
+        """parts[i] = rank i's tensor; returns per rank the stacked [world, ...] tensor."""
+        import torch
+        g = torch.stack(list(parts), 0)
+        return [g for _ in parts]
+
+    def all_reduce_sum(self, parts):
+        acc = parts[0].clone()
+        for p in parts[1:]:
+            acc += p
+        for p in parts:
+            p.copy_(acc)
+
+
+class DistComm(object):
+    """One rank per process over torch.distributed (NCCL on GPUs; gloo for the CPU tests of the plumbing)."""
+
+    def __init__(self):
+        import torch.distributed as dist
+        self.dist = dist
+        self.world = dist.get_world_size()
+        self.rank = dist.get_rank()
+
+    def exchange(self, sends, recvs):
+        dist = self.dist
+        send, recv = sends[0], recvs[0]
+        recv[self.rank].copy_(send[self.rank])
+        ops = []
+        for j in range(self.world):
+            if j != self.rank:
+                ops.append(dist.P2POp(dist.irecv, recv[j], j))
+        for j in range(self.world):
+            if j != self.rank:
+                ops.append(dist.P2POp(dist.isend, send[j], j))
+        if ops:
+            for w in dist.batch_isend_irecv(ops):          # one ncclGroupStart/End: an all-to-all over NVLink
+                w.wait()
+
+    def all_gather(self, parts):
+        import torch
+        t = parts[0].contiguous()
+        out = torch.empty((self.world,) + tuple(t.shape), dtype=t.dtype, device=t.device)
+        self.dist.all_gather_into_tensor(out, t) if t.is_cuda else self.dist.all_gather(list(out.unbind(0)), t)
+        return [out]
+
+    def all_reduce_sum(self, parts):
+        self.dist.all_reduce(parts[0], op=self.dist.ReduceOp.SUM)
+
+
+# ---------------------------------------------------------------------------------------------- one rank
+def _copy3d(src, src_off, dst, dst_off, n0, n1, n2, ss0, ss1, ds0, ds1):
+    """mccnn_copy3d on two float32 device tensors; offsets and strides in 16-byte granules."""
+    _ffi.call("mccnn_copy3d", ctypes.c_void_p(src.data_ptr() + 16 * int(src_off)),
+              ctypes.c_void_p(dst.data_ptr() + 16 * int(dst_off)), int(n0), int(n1), int(n2), int(ss0), int(ss1),
+              int(ds0), int(ds1), _ffi.stream_ptr())
+
+
+class SlabRank(object):
+    """Buffers and C-ABI calls of one rank of the partition."""
+
+    def __init__(self, plan, rank, checkpoint=None, cbca_mode=None, **hp):
+        torch = _pf._torch()
+        self.torch = torch
+        self.plan, self.rank = plan, int(rank)
+        self.hp = dict(DEFAULTS)
+        self.hp.update(hp)
+        H, W, D, N = plan.H, plan.W, plan.D, plan.world
+        assert D >= 2 and W >= D + 2, "need ndisp >= 2 and W >= ndisp + 2 (pf:94-95, :547-566)"
+        dev = _pf._dev()
+        f32 = torch.float32
+        e = lambda *shape, dtype=f32: torch.empty(shape, dtype=dtype, device=dev)
+        self.pad = (int(self.hp["patch_size"]) - 1) // 2
+        self.weights = _pf.resolve_weights(checkpoint, num_layers=self.pad)
+        self.Dl, self.Dlp = plan.d_count(rank), 4 * plan.g_count(rank)
+        self.dbase = plan.d_base(rank)
+        self.Dp = 4 * plan.G
+        self.h0, self.h1 = plan.rows[rank]
+        self.w0, self.w1 = plan.cols[rank]
+        Hr, Wc = self.h1 - self.h0, self.w1 - self.w0
+        self.img = [e(H, W), e(H, W)]
+        self.feat = [e(H, W, 64), e(H, W, 64)]
+        nb = int(_ffi.lib().mccnn_features_scratch_bytes(H, W, self.pad, self.pad))
+        self.feat_scratch = e((nb + 3) // 4)
+        # d-slab volumes (A: cost volume / CBCA2 output, B: CBCA1 output and SGM result, S: CBCA scratch)
+        self.volA = [e(H, W, self.Dlp), e(H, W, self.Dlp)]
+        self.volB = [e(H, W, self.Dlp), e(H, W, self.Dlp)]
+        self.volS = e(H, W, self.Dlp)
+        # the same cells as row slabs (all disparities of rows [h0, h1)) and column slabs (columns [w0, w1))
+        self.rowv = [e(Hr, W, self.Dp), e(Hr, W, self.Dp)]
+        self.colv = [e(H, Wc, self.Dp), e(H, Wc, self.Dp)]
+        # exchange staging: every re-partition moves exactly one slab's worth of cells out and in
+        nstage = max(H * W * self.Dlp, Hr * W * self.Dp, H * Wc * self.Dp)
+        self.stage_out = e(nstage)
+        self.stage_in = e(nstage)
+        self.arms = [e(H, W, 4, dtype=torch.uint8), e(H, W, 4, dtype=torch.uint8)]
+        self.count = [e(H, W, dtype=torch.int32), e(H, W, dtype=torch.int32)]
+        self.cbca_ws = _pf.cbca_workspace(H, W)
+        ns = int(_ffi.lib().mccnn_sgm_scratch_bytes(H, W, D))
+        self.sgm_flags = e((ns + 3) // 4, dtype=torch.int32)
+        self.wta_local = e(4, H, W)                        # (disp L, min L, disp R, min R) of this slab
+        self.disp = [e(H, W), e(H, W)]
+        self.tmp = [e(H, W), e(H, W)]
+        self.triple = e(3, H, W)
+        self.labels = e(H, W, dtype=torch.int32)
+        self.table = _pf._to_dev(_pf.bilateral_table(5, 5, 0, self.hp["blur_sigma"]))
+        self.cbca_mode = _pf.CBCA_MODE if cbca_mode is None else int(cbca_mode)
+        self.result = None
+
+    def set_images(self, left_image, right_image):
+        for i, im in enumerate((left_image, right_image)):
+            self.img[i].copy_(_pf._image2d(im))
+
+    # ---- phases --------------------------------------------------------------------------------
+    def front(self):
+        """features, this slab of the cost volume, cross arms, CBCA x iters1 (match.py:132-143)."""
+        p, call, sp, hp, pl = _ffi.ptr, _ffi.call, _ffi.stream_ptr, self.hp, self.plan
+        H, W, D = pl.H, pl.W, pl.D
+        for i in range(2):
+            call("mccnn_features", p(self.img[i]), H, W, self.pad, self.pad, self.weights.w_table, self.weights.b_table,
+                 p(self.feat[i]), p(self.feat_scratch), sp())
+        call("mccnn_cost_volume_slab", p(self.feat[0]), p(self.feat[1]), p(self.volA[0]), p(self.volA[1]), H, W, 64, D,
+             self.dbase, self.Dl, sp())
+        for i in range(2):
+            call("mccnn_cross_arms", p(self.img[i]), p(self.arms[i]), p(self.count[i]), H, W,
+                 ctypes.c_float(np.float32(hp["cbca_intensity"])), int(hp["cbca_distance"]), sp())
+        self._cbca(self.volA, self.volB, int(hp["cbca_num_iterations1"]))
+
+    def _cbca(self, src, dst, iters):
+        p, call, sp, hp, pl = _ffi.ptr, _ffi.call, _ffi.stream_ptr, self.hp, self.plan
+        for i in range(2):
+            call("mccnn_cbca", p(src[i]), p(dst[i]), p(self.volS), p(self.arms[i]), p(self.count[i]), self.Dl, pl.H, pl.W,
+                 iters, int(hp["cbca_distance"]), int(self.cbca_mode), p(self.cbca_ws), sp())
+
+    def _views(self, flat, shapes):
+        out, off = [], 0
+        for shp in shapes:
+            n = int(np.prod(shp))
+            out.append(flat[off:off + n].view(*shp))
+            off += n
+        return out
+
+    # d-slabs -> row slabs: block for rank j = its rows of my slab (already contiguous)
+    def send_rows(self, v):
+        return [self.volB[v][lo:hi] for lo, hi in self.plan.rows]
+
+    def recv_rows(self, v):
+        pl = self.plan
+        Hr = self.h1 - self.h0
+        return self._views(self.stage_in, [(Hr, pl.W, 4 * pl.g_count(j)) for j in range(pl.world)])
+
+    def unpack_rows(self, v, blocks):
+        pl = self.plan
+        n = (self.h1 - self.h0) * pl.W
+        for j, blk in enumerate(blocks):
+            gj = pl.g_count(j)
+            _copy3d(blk, 0, self.rowv[v], pl.granules[j][0], 1, n, gj, 0, gj, 0, pl.G)
+
+    def sgm_rows(self):
+        """(0,1) then (0,-1), pf:195-198, on rows [h0, h1)."""
+        p, call, sp, hp, pl = _ffi.ptr, _ffi.call, _ffi.stream_ptr, self.hp, self.plan
+        off = 4 * self.h0 * pl.W
+        il = ctypes.c_void_p(self.img[0].data_ptr() + off)
+        ir = ctypes.c_void_p(self.img[1].data_ptr() + off)
+        call("mccnn_sgm_passes_slab", p(self.rowv[0]), p(self.rowv[1]), il, ir, p(self.sgm_flags), pl.D,
+             self.h1 - self.h0, pl.W, 0, pl.W, 0, float(hp["sgm_P1"]), float(hp["sgm_P2"]), float(hp["sgm_Q1"]),
+             float(hp["sgm_Q2"]), float(hp["sgm_D"]), float(hp["sgm_V"]), sp())
+
+    # row slabs -> column slabs: block for rank j = its columns of my rows (packed), lands as rows of its slab
+    def send_cols(self, v):
+        pl = self.plan
+        Hr = self.h1 - self.h0
+        views = self._views(self.stage_out, [(Hr, pl.w_count(j), self.Dp) for j in range(pl.world)])
+        for j, blk in enumerate(views):
+            wj = pl.w_count(j)
+            _copy3d(self.rowv[v], pl.cols[j][0] * pl.G, blk, 0, Hr, wj, pl.G, pl.W * pl.G, pl.G, wj * pl.G, pl.G)
+        return views
+
+    def recv_cols(self, v):
+        return [self.colv[v][lo:hi] for lo, hi in self.plan.rows]
+
+    def sgm_cols(self):
+        """(-1,0) then (1,0), pf:203-208, on columns [w0, w1)."""
+        p, call, sp, hp, pl = _ffi.ptr, _ffi.call, _ffi.stream_ptr, self.hp, self.plan
+        call("mccnn_sgm_passes_slab", p(self.colv[0]), p(self.colv[1]), p(self.img[0]), p(self.img[1]), p(self.sgm_flags),
+             pl.D, pl.H, pl.W, self.w0, self.w1 - self.w0, 1, float(hp["sgm_P1"]), float(hp["sgm_P2"]),
+             float(hp["sgm_Q1"]), float(hp["sgm_Q2"]), float(hp["sgm_D"]), float(hp["sgm_V"]), sp())
+
+    # column slabs -> d-slabs: block for rank j = its disparities of my columns (packed); unpacked into columns
+    def send_slabs(self, v):
+        pl = self.plan
+        Wc = self.w1 - self.w0
+        views = self._views(self.stage_out, [(pl.H, Wc, 4 * pl.g_count(j)) for j in range(pl.world)])
+        for j, blk in enumerate(views):
+            gj = pl.g_count(j)
+            _copy3d(self.colv[v], pl.granules[j][0], blk, 0, 1, pl.H * Wc, gj, 0, pl.G, 0, gj)
+        return views
+
+    def recv_slabs(self, v):
+        pl = self.plan
+        return self._views(self.stage_in, [(pl.H, pl.w_count(j), self.Dlp) for j in range(pl.world)])
+
+    def unpack_slabs(self, v, blocks):
+        pl = self.plan
+        gl = pl.g_count(self.rank)
+        for j, blk in enumerate(blocks):
+            wj = pl.w_count(j)
+            _copy3d(blk, 0, self.volB[v], pl.cols[j][0] * gl, pl.H, wj, gl, wj * gl, gl, pl.W * gl, gl)
+
+    def back(self):
+        """CBCA x iters2 and this slab's winners (match.py:154-159)."""
+        p, call, sp, pl = _ffi.ptr, _ffi.call, _ffi.stream_ptr, self.plan
+        self._cbca(self.volB, self.volA, int(self.hp["cbca_num_iterations2"]))
+        for i in range(2):
+            call("mccnn_wta_slab", p(self.volA[i]), p(self.wta_local[2 * i]), p(self.wta_local[2 * i + 1]), self.Dl, pl.H,
+                 pl.W, self.dbase, sp())
+        return self.wta_local
+
+    def combine(self, gathered):
+        """gathered [world][4][H][W]: first minimum in slab order, then LR check / interpolation (match.py:163)."""
+        p, call, sp, pl = _ffi.ptr, _ffi.call, _ffi.stream_ptr, self.plan
+        P = pl.H * pl.W
+        base = gathered.data_ptr()
+        for i in range(2):
+            disps = ctypes.c_void_p(base + 4 * (2 * i) * P)
+            mins = ctypes.c_void_p(base + 4 * (2 * i + 1) * P)
+            call("mccnn_wta_combine", mins, disps, p(self.disp[i]), pl.world, 4 * P, pl.H, pl.W, sp())
+        call("mccnn_lr_interp", p(self.disp[0]), p(self.disp[1]), p(self.tmp[0]), p(self.labels), pl.H, pl.W, pl.D, sp())
+        call("mccnn_subpixel_gather", p(self.tmp[0]), p(self.volA[0]), p(self.triple), self.Dl, pl.H, pl.W, self.dbase,
+             pl.D, sp())
+        return self.triple
+
+    def finish(self):
+        """sub-pixel from the summed triple, median, bilateral (match.py:167-175)."""
+        p, call, sp, pl, hp = _ffi.ptr, _ffi.call, _ffi.stream_ptr, self.plan, self.hp
+        call("mccnn_subpixel_triple", p(self.tmp[0]), p(self.triple), p(self.tmp[1]), pl.D, pl.H, pl.W, sp())
+        call("mccnn_median", p(self.tmp[1]), p(self.tmp[0]), pl.H, pl.W, 5, 5, sp())
+        call("mccnn_bilateral", p(self.img[0]), p(self.tmp[0]), p(self.tmp[1]), p(self.table), pl.H, pl.W, 5, 5,
+             ctypes.c_float(np.float32(hp["blur_threshold"])), sp())
+        self.result = self.tmp[1]
+        return self.result
+
+
+def run_slabs(ranks, comm):
+    """Drive the ranks held by this process (one under torch.distributed, all of them with LocalComm) through the
+    pipeline; returns each rank's final disparity map (identical on every rank)."""
+    for r in ranks:
+        r.front()
+    for v in range(2):
+        sends = [r.send_rows(v) for r in ranks]
+        recvs = [r.recv_rows(v) for r in ranks]
+        comm.exchange(sends, recvs)
+        for r, blocks in zip(ranks, recvs):
+            r.unpack_rows(v, blocks)
+    for r in ranks:
+        r.sgm_rows()
+    for v in range(2):
+        comm.exchange([r.send_cols(v) for r in ranks], [r.recv_cols(v) for r in ranks])
+    for r in ranks:
+        r.sgm_cols()
+    for v in range(2):
+        sends = [r.send_slabs(v) for r in ranks]
+        recvs = [r.recv_slabs(v) for r in ranks]
+        comm.exchange(sends, recvs)
+        for r, blocks in zip(ranks, recvs):
+            r.unpack_slabs(v, blocks)
+    gathered = comm.all_gather([r.back() for r in ranks])
+    comm.all_reduce_sum([r.combine(g) for r, g in zip(ranks, gathered)])
+    return [r.finish() for r in ranks]
+
+
+class SlabMatcher(object):
+    """This process's rank of a disparity-slab partitioned pair under torch.distributed."""
+
+    def __init__(self, H, W, ndisp, checkpoint=None, **hp):
+        self.comm = DistComm()
+        self.plan = SlabPlan(H, W, ndisp, self.comm.world)
+        self.rank = SlabRank(self.plan, self.comm.rank, checkpoint=checkpoint, **hp)
+        self.H, self.W, self.D = self.plan.H, self.plan.W, self.plan.D
+        self.hp = self.rank.hp
+
+    def set_images(self, left_image, right_image):
+        self.rank.set_images(left_image, right_image)
+
+    def run(self):
+        return run_slabs([self.rank], self.comm)[0]
