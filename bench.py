@@ -3,6 +3,9 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c3|c2|c1] [--impl ours|reference]
 
+Workloads c5 / c5s are ONE pair shared by all ranks (disparity-slab partition with NVLink re-partitioning around
+SGM, mc-cnn-python_b200/slab.py; strong scaling); the others are one pair per rank.
+
 One "step" = one pass of the hot path (match.py:131-175: features -> cost volume -> CBCA x2 ->
 4 chained SGM passes -> CBCA x16 -> WTA -> LR-check/interpolation -> sub-pixel -> median ->
 bilateral) over one synthetic stereo pair per rank.  metric = H*W*D cells per second, whole job
@@ -36,7 +39,12 @@ WORKLOADS = {
     "c3": (1024, 1024, 192, None, "1024x1024x192 synthetic pair, full pipeline (features+CV+CBCA2+SGM4+CBCA16+WTA+refine)"),
     "c2": (512, 512, 128, ("cost_volume", "wta"), "512x512x128 synthetic pair, cost volume + WTA only"),
     "c1": (128, 128, 32, None, "128x128x32 synthetic pair, full pipeline"),
+    "c4": (1000, 1500, 256, None, "Middlebury-v3 half-res shaped pairs (1000x1500x256), full pipeline, one pair per GPU"),
+    # one big pair: a single GPU runs it whole, N > 1 GPUs share it by disparity slab (strong scaling)
+    "c5": (2000, 3000, 400, None, "2000x3000x400 single pair, full pipeline, disparity-slab partition across the GPUs"),
+    "c5s": (1024, 1536, 256, None, "1024x1536x256 single pair, full pipeline, disparity-slab partition across the GPUs"),
 }
+SINGLE_PAIR = ("c5", "c5s")
 METRIC = "cost_volume_cells_per_sec"
 UNIT = "cells/s"
 
@@ -198,8 +206,13 @@ def run_ours(args):
     ffi = pkg._ffi
     H, W, D, stages, desc = WORKLOADS[args.workload]
     full = stages is None
-    m = pkg.StereoMatcher(H, W, D, checkpoint=None, **({} if full else {"stages": stages}))
-    li, ri = synth_pair(H, W, min(37, D // 4), seed=rank)      # one pair per rank
+    single_pair = args.workload in SINGLE_PAIR
+    slab = single_pair and world > 1
+    if slab:
+        m = pkg.SlabMatcher(H, W, D, checkpoint=None)
+    else:
+        m = pkg.StereoMatcher(H, W, D, checkpoint=None, **({} if full else {"stages": stages}))
+    li, ri = synth_pair(H, W, min(37, D // 4), seed=0 if single_pair else rank)      # one pair per rank / one for all
     m.set_images(li, ri)
     if not full:
         m.set_features(*unit_features(H, W, seed=rank))
@@ -242,17 +255,20 @@ def run_ours(args):
         ms, e2e_ms = float(t[0]), float(t[1])
 
     cells = float(H) * W * D
-    value = world * cells * args.steps / (ms * 1e-3)
-    e2e_value = world * cells * args.steps / (e2e_ms * 1e-3)
+    pairs = 1 if single_pair else world
+    value = pairs * cells * args.steps / (ms * 1e-3)
+    e2e_value = pairs * cells * args.steps / (e2e_ms * 1e-3)
 
     line = None
-    if rank == 0:
-        # per-stage device times (CUDA events on the launching stream), averaged over a few passes
-        reps = 3
-        acc = {}
+    # per-stage device times (CUDA events on the launching stream), averaged over a few passes; the slab
+    # partition's passes are collective, so every rank makes them (rank 0's times are reported)
+    reps = 3
+    acc = {}
+    if rank == 0 or slab:
         for _ in range(reps):
             for k, v in m.run_timed().items():
                 acc[k] = acc.get(k, 0.0) + v / reps
+    if rank == 0:
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -262,10 +278,16 @@ def run_ours(args):
         peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
         hp = m.hp
         it1, it2 = int(hp["cbca_num_iterations1"]), int(hp["cbca_num_iterations2"])
+        if slab:
+            cells_rank = cells / world                       # this rank's slab of every volume
         # algorithmic bytes per stage and launches of the stage's main kernel
         # ("launch" of a CBCA round = its two streaming passes k_cbca_rows + k_cbca_cols on one volume; the
         #  algorithmic figure is the fused minimum of 8 B/cell/round, the two passes actually move 16 B/cell)
         model = {
+            "cbca2": (8.0 * cells_rank * it2 * 2, it2 * 2, "k_cbca_rows+k_cbca_cols"),
+            "sgm_rows": (8.0 * cells_rank * 2 * 2, 2, "k_sgm_pass"),
+            "sgm_cols": (8.0 * cells_rank * 2 * 2, 2, "k_sgm_pass"),
+        } if slab else {
             "cost_volume": ((8.0 + 512.0 / D) * cells, 1, "k_cost_volume_tc (+k_cost_fill)"),
             "cbca1": (8.0 * cells * it1 * 2, it1 * 2, "k_cbca_rows+k_cbca_cols"),
             "sgm": (8.0 * cells * 4 * 2, 4, "k_sgm_pass"),
@@ -297,13 +319,15 @@ def run_ours(args):
                     "algorithmic_bytes_per_launch": nbytes / nl, "avg_launch_ms": acc[dom] / nl}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": desc, "H": H, "W": W, "D": D, "pairs_per_step": world,
-                           "parallelism": "image-pair data parallel, dp%d" % world,
+                "scaling": "strong" if single_pair else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": desc, "H": H, "W": W, "D": D, "pairs_per_step": pairs,
+                           "parallelism": ("one pair, %d disparity slabs; row / column slabs around SGM (3 NVLink "
+                                           "re-partitions per volume)" % world) if slab else
+                                          "image-pair data parallel, dp%d" % world,
                            "weights": "random-init (glorot-uniform, seed 0)",
                            "l2": "no explicit flush: each stage streams >= 1.6 GB (volumes are 805 MB each) >> 126 MB L2"},
-                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": m.h2d_bytes,
-                        "d2h_bytes_per_step": m.d2h_bytes, "ms_per_step": e2e_ms / args.steps},
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 2 * H * W * 4,
+                        "d2h_bytes_per_step": H * W * 4, "ms_per_step": e2e_ms / args.steps},
                 "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
                 "stages_ms": acc, "kernels": kernels}
         if world == 1 and not args.no_cpu_baseline:

@@ -302,10 +302,13 @@ class SlabRank(object):
             wj = pl.w_count(j)
             _copy3d(blk, 0, self.volB[v], pl.cols[j][0] * gl, pl.H, wj, gl, wj * gl, gl, pl.W * gl, gl)
 
-    def back(self):
-        """CBCA x iters2 and this slab's winners (match.py:154-159)."""
-        p, call, sp, pl = _ffi.ptr, _ffi.call, _ffi.stream_ptr, self.plan
+    def cbca2(self):
+        """CBCA x iters2 (match.py:154-155)."""
         self._cbca(self.volB, self.volA, int(self.hp["cbca_num_iterations2"]))
+
+    def wta(self):
+        """This slab's winners and their costs (match.py:159)."""
+        p, call, sp, pl = _ffi.ptr, _ffi.call, _ffi.stream_ptr, self.plan
         for i in range(2):
             call("mccnn_wta_slab", p(self.volA[i]), p(self.wta_local[2 * i]), p(self.wta_local[2 * i + 1]), self.Dl, pl.H,
                  pl.W, self.dbase, sp())
@@ -336,32 +339,51 @@ class SlabRank(object):
         return self.result
 
 
-def run_slabs(ranks, comm):
+def run_slabs(ranks, comm, marks=None):
     """Drive the ranks held by this process (one under torch.distributed, all of them with LocalComm) through the
-    pipeline; returns each rank's final disparity map (identical on every rank)."""
+    pipeline; returns each rank's final disparity map (identical on every rank).  `marks`, if a list, receives
+    (phase name, CUDA event recorded after the phase) pairs."""
+    def mark(name):
+        if marks is not None:
+            ev = ranks[0].torch.cuda.Event(enable_timing=True)
+            ev.record()
+            marks.append((name, ev))
+
+    mark("start")
     for r in ranks:
         r.front()
+    mark("front")
     for v in range(2):
         sends = [r.send_rows(v) for r in ranks]
         recvs = [r.recv_rows(v) for r in ranks]
         comm.exchange(sends, recvs)
         for r, blocks in zip(ranks, recvs):
             r.unpack_rows(v, blocks)
+    mark("to_rows")
     for r in ranks:
         r.sgm_rows()
+    mark("sgm_rows")
     for v in range(2):
         comm.exchange([r.send_cols(v) for r in ranks], [r.recv_cols(v) for r in ranks])
+    mark("to_cols")
     for r in ranks:
         r.sgm_cols()
+    mark("sgm_cols")
     for v in range(2):
         sends = [r.send_slabs(v) for r in ranks]
         recvs = [r.recv_slabs(v) for r in ranks]
         comm.exchange(sends, recvs)
         for r, blocks in zip(ranks, recvs):
             r.unpack_slabs(v, blocks)
-    gathered = comm.all_gather([r.back() for r in ranks])
+    mark("to_slabs")
+    for r in ranks:
+        r.cbca2()
+    mark("cbca2")
+    gathered = comm.all_gather([r.wta() for r in ranks])
     comm.all_reduce_sum([r.combine(g) for r, g in zip(ranks, gathered)])
-    return [r.finish() for r in ranks]
+    out = [r.finish() for r in ranks]
+    mark("wta_refine")
+    return out
 
 
 class SlabMatcher(object):
@@ -379,3 +401,28 @@ class SlabMatcher(object):
 
     def run(self):
         return run_slabs([self.rank], self.comm)[0]
+
+    def run_timed(self):
+        """run() with a CUDA event after every phase: {phase: milliseconds} on this rank."""
+        marks = []
+        run_slabs([self.rank], self.comm, marks)
+        self.rank.torch.cuda.synchronize()
+        return {name: marks[i - 1][1].elapsed_time(ev) for i, (name, ev) in enumerate(marks) if i > 0}
+
+    def run_host(self, left_image, right_image):
+        """NumPy images in, NumPy disparity out (every rank uploads the pair, every rank ends with the map)."""
+        torch = self.rank.torch
+        if not hasattr(self, "_host_in"):
+            H, W = self.H, self.W
+            self._host_in = [torch.empty((H, W), dtype=torch.float32, pin_memory=True) for _ in range(2)]
+            self._host_out = torch.empty((H, W), dtype=torch.float32, pin_memory=True)
+        for i, im in enumerate((left_image, right_image)):
+            a = np.asarray(im, dtype=np.float32)
+            if a.ndim == 3:
+                a = a[:, :, 0]
+            self._host_in[i].numpy()[...] = a
+            self.rank.img[i].copy_(self._host_in[i], non_blocking=True)
+        d = self.run()
+        self._host_out.copy_(d, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return self._host_out.numpy().copy()
