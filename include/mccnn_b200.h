@@ -88,10 +88,13 @@ int mccnn_cross_region_list(const uint8_t *arms, int32_t *region, int H, int W,
  * mode MCCNN_CBCA_SEPARABLE_MARCH: the same sums in one row-marching kernel per round (TMA-staged rows, row
  *      sums kept in a thread-private shared-memory ring): every cell read once and written once.  Shapes it
  *      is not built for (distance_threshold > 14, D < 29) take the two streaming passes instead.
+ * mode MCCNN_CBCA_SEPARABLE_L2: the two streaming passes as one persistent kernel per round, pipelined over
+ *      bands of 8 rows so that the row sums stay in a 64-row ring in L2 (the first rows of `scratch`) instead of
+ *      making a round trip through HBM.  Bit-identical to MCCNN_CBCA_SEPARABLE; needs the workspace.
  * mode MCCNN_CBCA_EXACT: one float32 running sum over the whole region in the reference's enumeration
  *      order (pf:149-163), bit-identical to the reference (<= 729 additions per cell). */
 enum mccnn_cbca_mode { MCCNN_CBCA_SEPARABLE = 0, MCCNN_CBCA_EXACT = 1, MCCNN_CBCA_SEPARABLE_TILED = 2,
-                       MCCNN_CBCA_SEPARABLE_MARCH = 3 };
+                       MCCNN_CBCA_SEPARABLE_MARCH = 3, MCCNN_CBCA_SEPARABLE_L2 = 4 };
 size_t mccnn_cbca_workspace_bytes(int H, int W);
 int mccnn_cbca(const float *in, float *out, float *scratch, const uint8_t *arms,
                const int32_t *count, int D, int H, int W, int iters, int distance_threshold, int mode,

@@ -11,6 +11,7 @@
 #include "cbca_tile.cuh"
 #include "cbca_stream.cuh"
 #include "cbca_march.cuh"
+#include "cbca_fused.cuh"
 #include <stdlib.h>
 
 namespace mccnn {
@@ -238,13 +239,16 @@ static const int CBCA_MAX_ROUNDS = 1024;       // one tile counter per round of 
 
 size_t mccnn_cbca_workspace_bytes(int H, int W) {
     if (H < 1 || W < 1) return 0;
-    return (size_t)cdiv(W, CT_TW) * cdiv(H, CT_TH) * sizeof(CbcaTileMeta) + CBCA_MAX_ROUNDS * sizeof(unsigned);
+    // tiled mode: per-tile schedule + one tile counter per round; L2 mode: ticket + two completion counters per band per round
+    const size_t tiled = (size_t)cdiv(W, CT_TW) * cdiv(H, CT_TH) * sizeof(CbcaTileMeta) + CBCA_MAX_ROUNDS * sizeof(unsigned);
+    const size_t fused = (size_t)CBCA_MAX_ROUNDS * (1 + 2 * (size_t)cdiv(H, CS_PH)) * sizeof(unsigned);
+    return tiled > fused ? tiled : fused;
 }
 
 int mccnn_cbca(const float *in, float *out, float *scratch, const uint8_t *arms, const int32_t *count, int D, int H,
                int W, int iters, int dist, int mode, void *workspace, void *stream) {
     MCCNN_REQUIRE(mode == MCCNN_CBCA_SEPARABLE || mode == MCCNN_CBCA_EXACT || mode == MCCNN_CBCA_SEPARABLE_TILED ||
-                      mode == MCCNN_CBCA_SEPARABLE_MARCH,
+                      mode == MCCNN_CBCA_SEPARABLE_MARCH || mode == MCCNN_CBCA_SEPARABLE_L2,
                   "cbca: unknown mode %d", mode);
     MCCNN_REQUIRE(dist >= 1 && dist <= 255, "cbca: distance_threshold %d outside [1, 255]", dist);
     MCCNN_REQUIRE(mode != MCCNN_CBCA_SEPARABLE_TILED || dist <= CT_MAXARM + 1,
@@ -259,8 +263,11 @@ int mccnn_cbca(const float *in, float *out, float *scratch, const uint8_t *arms,
     const int Dp = dpitch(D), G = Dp / 4;
     // the marching kernel's boxes are 8 granules x up to 13 halo pixels: other shapes take the two streaming passes
     if (mode == MCCNN_CBCA_SEPARABLE_MARCH && (dist > CM_ARM + 1 || G < CM_GT)) mode = MCCNN_CBCA_SEPARABLE;
-    MCCNN_REQUIRE(iters < (mode == MCCNN_CBCA_SEPARABLE ? 1 : 2) || (scratch && scratch != in && scratch != out),
+    const bool two_pass = mode == MCCNN_CBCA_SEPARABLE || mode == MCCNN_CBCA_SEPARABLE_L2;
+    MCCNN_REQUIRE(iters < (two_pass ? 1 : 2) || (scratch && scratch != in && scratch != out),
                   "cbca: scratch volume required (separable: any round; other modes: iters >= 2)");
+    MCCNN_REQUIRE(mode != MCCNN_CBCA_SEPARABLE_L2 || iters == 0 || (workspace && iters <= CBCA_MAX_ROUNDS),
+                  "cbca: L2 mode needs a workspace of mccnn_cbca_workspace_bytes(H, W) bytes and at most %d rounds", CBCA_MAX_ROUNDS);
     if (iters == 0) {
         MCCNN_CUDA(cudaMemcpyAsync(out, in, (size_t)H * W * Dp * sizeof(float), cudaMemcpyDeviceToDevice, s));
         return MCCNN_OK;
@@ -276,6 +283,40 @@ int mccnn_cbca(const float *in, float *out, float *scratch, const uint8_t *arms,
             k_cbca_cols<<<sgrid, CS_THREADS, 0, s>>>(reinterpret_cast<const float4 *>(scratch), reinterpret_cast<float4 *>(out),
                                                       reinterpret_cast<const uchar4 *>(arms), count, G, H, W);
             MCCNN_LAUNCHED("cbca_cols");
+            src = out;
+        }
+        return MCCNN_OK;
+    }
+    if (mode == MCCNN_CBCA_SEPARABLE_L2) {
+        // one persistent kernel per round; row sums in the first min(H, 64) rows of scratch, which stay in L2
+        static int fused_grid = 0;
+        if (fused_grid == 0) {
+            int dev = 0, sms = 0, per_sm = 0;
+            MCCNN_CUDA(cudaGetDevice(&dev));
+            MCCNN_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+            MCCNN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_cbca_fused, CS_THREADS, 0));
+            fused_grid = sms * (per_sm > 0 ? per_sm : 1);
+        }
+        CfSched sc;
+        sc.nbx = cdiv(W, CS_PW); sc.nz = cdiv(G, CS_GC); sc.nb = cdiv(H, CS_PH);
+        sc.lag = sc.nb < CF_LAG ? sc.nb : CF_LAG;
+        sc.items_band = sc.nbx * sc.nz;
+        sc.chunk = 1;
+        if (const char *e = getenv("MCCNN_CBCA_L2_CHUNK")) { const int c = atoi(e); if (c >= 1 && c <= 64) sc.chunk = c; }
+        sc.chunks_band = cdiv(sc.items_band, sc.chunk);
+        const long long total = 2ll * sc.nb * sc.chunks_band;
+        MCCNN_REQUIRE(total < (1ll << 31), "cbca: image too large");
+        sc.total = (int)total;
+        const size_t per_round = 1 + 2 * (size_t)sc.nb;
+        unsigned *counters = reinterpret_cast<unsigned *>(workspace);
+        MCCNN_CUDA(cudaMemsetAsync(counters, 0, (size_t)iters * per_round * sizeof(unsigned), s));
+        const int grid = total < fused_grid ? (int)total : fused_grid;
+        const float *src = in;
+        for (int it = 0; it < iters; it++) {
+            k_cbca_fused<<<grid, CS_THREADS, 0, s>>>(reinterpret_cast<const float4 *>(src), reinterpret_cast<float4 *>(scratch),
+                                                     reinterpret_cast<float4 *>(out), reinterpret_cast<const uchar4 *>(arms), count,
+                                                     G, H, W, sc, counters + (size_t)it * per_round);
+            MCCNN_LAUNCHED("cbca_fused");
             src = out;
         }
         return MCCNN_OK;

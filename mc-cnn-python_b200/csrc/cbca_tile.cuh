@@ -275,7 +275,6 @@ __device__ __forceinline__ void ct_issue_slab(const CtMaps &maps, const CbcaTile
                                               unsigned char *dst, unsigned long long *bar) {
     const int lane = threadIdx.x & 31;
     const int level = ct_level(m.gp);
-    ct_fence_proxy_async();                                     // earlier generic reads of dst are ordered by the barrier
     for (int r = lane; r < m.nrows; r += 32) {
         const int hi = m.hwi[r];
         ct_tma_load_3d(dst + (size_t)m.rowb[r] * 16, &maps.m[level][hi], 4 * g0, (int)m.w0 - ct_halo(hi), (int)m.r0 + r, bar);

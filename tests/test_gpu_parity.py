@@ -247,6 +247,24 @@ def test_cbca_march_mode_matches_streaming_mode_and_oracle(pf, oracle, monkeypat
         np.testing.assert_allclose(Lg, Lo, atol=CBCA_SEP_RTOL * 64, rtol=0)
 
 
+def test_cbca_l2_mode_matches_streaming_mode(pf, monkeypatch):
+    """MCCNN_CBCA_SEPARABLE_L2 (both passes in one persistent, band-pipelined kernel, row sums in a 64-row ring)
+    is the same arithmetic as the two streaming passes: identical bits, for images taller than the ring (ring rows
+    reused), shorter than a band, ragged widths / granule counts, flat images (13-row arms across bands)."""
+    cases = [(150, 90, 70, 4, 3), (200, 47, 192, 30, 2), (9, 29, 33, 1, 2), (70, 21, 40, 2, 3), (64, 64, 32, 1, 1),
+             (137, 200, 29, 3, 2), (5, 40, 100, 2, 2)]
+    for (H, W, D, levels, iters) in cases:
+        li, ri = synth_images(H * W + D, H, W, levels, 2)
+        rng = np.random.default_rng(D)
+        Lv = rng.standard_normal((D, H, W)).astype(np.float32) * 50
+        Rv = rng.standard_normal((D, H, W)).astype(np.float32) * 50
+        monkeypatch.setattr(pf, "CBCA_MODE", pf.CBCA_SEPARABLE)
+        Ls, Rs = pf.cost_volume_aggregation(li, ri, Lv, Rv, 0.02, 14, iters)
+        monkeypatch.setattr(pf, "CBCA_MODE", pf.CBCA_SEPARABLE_L2)
+        Lt, Rt = pf.cost_volume_aggregation(li, ri, Lv, Rv, 0.02, 14, iters)
+        assert eq(Ls, Lt) and eq(Rs, Rt), (H, W, D)
+
+
 def test_cbca_plane_constant_is_fixed_point(pf):
     """Property (any size): a volume that is constant per disparity plane with small-integer values is a
     fixed point of region averaging (exact sums, exact division)."""
