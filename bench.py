@@ -281,17 +281,17 @@ def run_ours(args):
         if slab:
             cells_rank = cells / world                       # this rank's slab of every volume
         # algorithmic bytes per stage and launches of the stage's main kernel
-        # ("launch" of a CBCA round = its two streaming passes k_cbca_rows + k_cbca_cols on one volume; the
+        # ("launch" of a CBCA round = its two streaming passes (k_cbca_pass, rows then columns) on one volume; the
         #  algorithmic figure is the fused minimum of 8 B/cell/round, the two passes actually move 16 B/cell)
         model = {
-            "cbca2": (8.0 * cells_rank * it2 * 2, it2 * 2, "k_cbca_rows+k_cbca_cols"),
+            "cbca2": (8.0 * cells_rank * it2 * 2, it2 * 2, "k_cbca_pass<rows>+k_cbca_pass<cols>"),
             "sgm_rows": (8.0 * cells_rank * 2 * 2, 2, "k_sgm_pass"),
             "sgm_cols": (8.0 * cells_rank * 2 * 2, 2, "k_sgm_pass"),
         } if slab else {
             "cost_volume": ((8.0 + 512.0 / D) * cells, 1, "k_cost_volume_tc (+k_cost_fill)"),
-            "cbca1": (8.0 * cells * it1 * 2, it1 * 2, "k_cbca_rows+k_cbca_cols"),
+            "cbca1": (8.0 * cells * it1 * 2, it1 * 2, "k_cbca_pass<rows>+k_cbca_pass<cols>"),
             "sgm": (8.0 * cells * 4 * 2, 4, "k_sgm_pass"),
-            "cbca2": (8.0 * cells * it2 * 2, it2 * 2, "k_cbca_rows+k_cbca_cols"),
+            "cbca2": (8.0 * cells * it2 * 2, it2 * 2, "k_cbca_pass<rows>+k_cbca_pass<cols>"),
             "wta": (4.0 * cells * 2, 2, "k_wta"),
         }
         kernels = {}

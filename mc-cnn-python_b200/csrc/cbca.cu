@@ -206,6 +206,19 @@ static int launch_march(const CmMaps &maps, float *dst, const uint8_t *arms, con
     return MCCNN_OK;
 }
 
+// One round of the default mode: row sums src -> scratch, column sums scratch -> out.
+static int stream_round(const float *src, float *scratch, float *out, const uint8_t *arms, const int32_t *count, int G, int H,
+                        int W, cudaStream_t s) {
+    dim3 grid(cdiv(W, CS_PW), cdiv(H, CS_PH), cdiv(G, CS_GC));
+    k_cbca_pass<false, CS_ITEMS, 1><<<grid, CS_THREADS, 0, s>>>(reinterpret_cast<const float4 *>(src), reinterpret_cast<float4 *>(scratch),
+                                                                reinterpret_cast<const uchar4 *>(arms), count, G, H, W);
+    MCCNN_LAUNCHED("cbca_rows");
+    k_cbca_pass<true, CS_ITEMS, 1><<<grid, CS_THREADS, 0, s>>>(reinterpret_cast<const float4 *>(scratch), reinterpret_cast<float4 *>(out),
+                                                               reinterpret_cast<const uchar4 *>(arms), count, G, H, W);
+    MCCNN_LAUNCHED("cbca_cols");
+    return MCCNN_OK;
+}
+
 }  // namespace mccnn
 
 using namespace mccnn;
@@ -274,15 +287,10 @@ int mccnn_cbca(const float *in, float *out, float *scratch, const uint8_t *arms,
     }
     if (mode == MCCNN_CBCA_SEPARABLE) {
         // every round: row sums src -> scratch, column sums scratch -> out; the next round reads out
-        dim3 sgrid(cdiv(W, CS_PW), cdiv(H, CS_PH), cdiv(G, CS_GC));
         const float *src = in;
         for (int it = 0; it < iters; it++) {
-            k_cbca_rows<<<sgrid, CS_THREADS, 0, s>>>(reinterpret_cast<const float4 *>(src), reinterpret_cast<float4 *>(scratch),
-                                                      reinterpret_cast<const uchar4 *>(arms), G, H, W);
-            MCCNN_LAUNCHED("cbca_rows");
-            k_cbca_cols<<<sgrid, CS_THREADS, 0, s>>>(reinterpret_cast<const float4 *>(scratch), reinterpret_cast<float4 *>(out),
-                                                      reinterpret_cast<const uchar4 *>(arms), count, G, H, W);
-            MCCNN_LAUNCHED("cbca_cols");
+            int rc = stream_round(src, scratch, out, arms, count, G, H, W, s);
+            if (rc) return rc;
             src = out;
         }
         return MCCNN_OK;

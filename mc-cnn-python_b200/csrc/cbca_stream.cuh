@@ -1,13 +1,12 @@
 // Separable cross-based aggregation as two streaming passes (default fast mode of mccnn_cbca).
 //
 // One round is  out(h,w) = ( sum_{h' in spine(h,w)} Hs(h',w) ) / |U(h,w)|,  Hs(h',w) = sum_{w' in arm(h',w)} in(h',w')
-// (pf:640-650): k_cbca_rows writes Hs, k_cbca_cols adds it along the spine and divides.  Both are pure
-// gathers with no shared memory and no barriers: the lanes of a warp are consecutive disparity granules of
-// one pixel (two pixels when a warp straddles a pixel boundary), so every load and store is a contiguous run
-// and an arm walk is warp uniform; neighbouring pixels are served by L1/L2 (a CTA covers an 8x4 pixel patch
-// per 64 disparities).  HBM traffic is 16 B per cell per round -- twice the fused minimum -- but the passes
-// run near copy speed, which the fused shared-memory kernel (cbca_tile.cuh) does not: its short
-// data-dependent phases are dominated by barrier waits (profiles/r1_cbca_round_tile.md).
+// (pf:640-650): k_cbca_pass<rows> writes Hs, k_cbca_pass<cols> adds it along the spine and divides.  Both are
+// pure gathers with no barriers: the lanes of a warp are consecutive disparity granules of one pixel (two
+// pixels per warp), so every load and store is a contiguous run and an arm walk is warp uniform; neighbouring
+// pixels are served by L2 (a CTA covers an 8x4 pixel patch per 64 disparities).  HBM traffic is 16 B per cell
+// per round -- twice the fused minimum -- but the passes run closer to copy speed than any of the fused
+// kernels tried (cbca_tile.cuh, cbca_march.cuh, cbca_fused.cuh: DESIGN.md 5.3).
 // Summation order inside a row and along the spine is the reference's; only the association
 // (row sums first) differs: ~1e-7 relative.
 #pragma once
@@ -15,7 +14,10 @@
 
 namespace mccnn {
 
-constexpr int CS_PH = 8, CS_PW = 4, CS_GC = 16, CS_THREADS = 128;   // patch 8x4 pixels x 16 granules per CTA (best of a sweep)
+constexpr int CS_PH = 8, CS_PW = 4, CS_GC = 16, CS_THREADS = 128;   // patch 8x4 pixels x 16 granules per CTA
+constexpr int CS_MIN_BLOCKS = 8;   // <= 64 registers: 8 CTAs per SM.  Measured at C3 (ms per round): 6 -> 0.673, 7 -> 0.628,
+                                   // 8 -> 0.608, 9 -> 0.647, 10 -> 0.740; other shapes (items per thread, staged
+                                   // neighbours): (4,1) 0.608, (3,1) 0.621, (2,1) 0.704, (4,2) 0.825, (2,2) 0.735; cp.async.ca 0.737
 
 __device__ __forceinline__ void cs_add(float4 &acc, const float4 v) {
     acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
@@ -28,44 +30,6 @@ __device__ __forceinline__ void cs_cp_async16(void *smem_dst, const void *gmem_s
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem_src));
 }
 
-// The centre cell and the two nearest neighbours of every item travel global -> shared with cp.async: bytes in
-// flight that cost no registers (these kernels are bound by memory-level parallelism, and most arms are 0 or 1 long,
-// so the common walk needs nothing else).  A thread reads back only its own slots: no barrier.
-__global__ void __launch_bounds__(CS_THREADS) k_cbca_rows(const float4 *__restrict__ in, float4 *__restrict__ hs,
-                                                          const uchar4 *__restrict__ arms, int G, int H, int W) {
-    __shared__ float4 stage[3][CS_ITEMS][CS_THREADS];            // [centre, left, right]: 24 KB
-    const int gi = threadIdx.x % CS_GC, g = blockIdx.z * CS_GC + gi;
-    if (g >= G) return;
-    int p[CS_ITEMS];
-    uchar4 a[CS_ITEMS];
-#pragma unroll
-    for (int s = 0; s < CS_ITEMS; s++) {
-        const int pi = s * (CS_THREADS / CS_GC) + threadIdx.x / CS_GC;
-        const int h = blockIdx.y * CS_PH + pi / CS_PW, w = blockIdx.x * CS_PW + pi % CS_PW;
-        p[s] = (h < H && w < W) ? h * W + w : -1;
-        if (p[s] >= 0) {
-            const float4 *c = in + (size_t)p[s] * G + g;
-            cs_cp_async16(&stage[0][s][threadIdx.x], c);
-            if (w > 0) cs_cp_async16(&stage[1][s][threadIdx.x], c - G);
-            if (w + 1 < W) cs_cp_async16(&stage[2][s][threadIdx.x], c + G);
-            a[s] = arms[p[s]];
-        }
-    }
-    asm volatile("cp.async.wait_all;\n" ::: "memory");
-#pragma unroll
-    for (int s = 0; s < CS_ITEMS; s++) {
-        if (p[s] < 0) continue;
-        const float4 *c = in + (size_t)p[s] * G + g;
-        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-        cs_add(acc, stage[0][s][threadIdx.x]);                                   // w, w-1, .., w-left (pf:645-650)
-        if (a[s].z >= 1) cs_add(acc, stage[1][s][threadIdx.x]);
-        for (int j = 2; j <= a[s].z; j++) cs_add(acc, c[-(ptrdiff_t)j * G]);
-        if (a[s].w >= 1) cs_add(acc, stage[2][s][threadIdx.x]);                  // w+1, .., w+right
-        for (int j = 2; j <= a[s].w; j++) cs_add(acc, c[(ptrdiff_t)j * G]);
-        hs[(size_t)p[s] * G + g] = acc;
-    }
-}
-
 // a / n for n = |U| (an integer <= 729), y = RN(1/n): q = RN(a*y); r = a - n*q (exact, FMA); RN(q + r*y):
 // correctly rounded (Markstein), i.e. the IEEE division of pf:161; odd magnitudes take the plain division.
 __device__ __forceinline__ float cs_div1(float a, float n, float y) {
@@ -74,45 +38,71 @@ __device__ __forceinline__ float cs_div1(float a, float n, float y) {
     return fmaf(r, y, q);
 }
 
-__global__ void __launch_bounds__(CS_THREADS) k_cbca_cols(const float4 *__restrict__ hs, float4 *__restrict__ out,
+// One pass, rows (COLS = false: Hs = sum along the row arm, stride one pixel) or columns (COLS = true: sum of Hs
+// along the spine, stride one image row, then / |U|).  A CTA is 128 threads = 16 granules x 8 pixel slots and covers
+// a (2 * ITEMS) x 4 pixel patch, ITEMS (pixel, granule) items per thread.  The centre cell and the NB nearest cells
+// on either side of every item travel global -> shared with cp.async: bytes in flight that cost no registers (these
+// kernels are bound by memory-level parallelism, and most arms are 0 or 1 long, so the common walk needs nothing
+// else).  A thread reads back only its own slots: no barrier.
+template <bool COLS, int ITEMS, int NB>
+__global__ void __launch_bounds__(CS_THREADS, CS_MIN_BLOCKS) k_cbca_pass(const float4 *__restrict__ src, float4 *__restrict__ dst,
                                                           const uchar4 *__restrict__ arms, const int32_t *__restrict__ count,
                                                           int G, int H, int W) {
+    __shared__ float4 stage[2 * NB + 1][ITEMS][CS_THREADS];      // [centre, -1, +1, -2, +2, ..]
+    constexpr int PH = 2 * ITEMS;
     const int gi = threadIdx.x % CS_GC, g = blockIdx.z * CS_GC + gi;
     if (g >= G) return;
-    const ptrdiff_t rs = (ptrdiff_t)W * G;
-    size_t p[CS_ITEMS];
-    bool ok[CS_ITEMS];
-    uchar4 a[CS_ITEMS];
-    float4 c0[CS_ITEMS];
-    float n[CS_ITEMS];
+    const ptrdiff_t stride = COLS ? (ptrdiff_t)W * G : (ptrdiff_t)G;
+    size_t p[ITEMS];
+    bool ok[ITEMS];
+    uchar4 a[ITEMS];
+    float n[ITEMS];
 #pragma unroll
-    for (int s = 0; s < CS_ITEMS; s++) {
+    for (int s = 0; s < ITEMS; s++) {
         const int pi = s * (CS_THREADS / CS_GC) + threadIdx.x / CS_GC;
-        const int h = blockIdx.y * CS_PH + pi / CS_PW, w = blockIdx.x * CS_PW + pi % CS_PW;
+        const int h = blockIdx.y * PH + pi / CS_PW, w = blockIdx.x * CS_PW + pi % CS_PW;
         ok[s] = h < H && w < W;
         p[s] = ok[s] ? (size_t)h * W + w : 0;
-        a[s] = arms[p[s]];
-        n[s] = (float)count[p[s]];
-        c0[s] = hs[p[s] * G + g];
-    }
+        if (ok[s]) {
+            const float4 *c = src + p[s] * G + g;
+            const int x = COLS ? h : w, lim = COLS ? H : W;
+            cs_cp_async16(&stage[0][s][threadIdx.x], c);
 #pragma unroll
-    for (int s = 0; s < CS_ITEMS; s++) {
-        if (!ok[s]) continue;
-        const float4 *c = hs + p[s] * G + g;
-        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-        cs_add(acc, c0[s]);                                                      // h, h-1, .., h-up (pf:640-644)
-        for (int k = 1; k <= a[s].x; k++) cs_add(acc, c[-k * rs]);
-        for (int k = 1; k <= a[s].y; k++) cs_add(acc, c[k * rs]);                // h+1, .., h+down
-        const float hi = fmaxf(fmaxf(fabsf(acc.x), fabsf(acc.y)), fmaxf(fabsf(acc.z), fabsf(acc.w)));
-        const float lo = fminf(fminf(fabsf(acc.x), fabsf(acc.y)), fminf(fabsf(acc.z), fabsf(acc.w)));
-        float4 r;
-        if (hi < 1e30f && lo > 1e-30f) {
-            const float y = 1.0f / n[s];
-            r = make_float4(cs_div1(acc.x, n[s], y), cs_div1(acc.y, n[s], y), cs_div1(acc.z, n[s], y), cs_div1(acc.w, n[s], y));
-        } else {
-            r = make_float4(acc.x / n[s], acc.y / n[s], acc.z / n[s], acc.w / n[s]);   // pf:161
+            for (int k = 1; k <= NB; k++) {
+                if (x - k >= 0) cs_cp_async16(&stage[2 * k - 1][s][threadIdx.x], c - k * stride);
+                if (x + k < lim) cs_cp_async16(&stage[2 * k][s][threadIdx.x], c + k * stride);
+            }
         }
-        out[p[s] * G + g] = r;
+        a[s] = arms[p[s]];
+        n[s] = COLS ? (float)count[p[s]] : 1.0f;
+    }
+    asm volatile("cp.async.wait_all;\n" ::: "memory");
+#pragma unroll
+    for (int s = 0; s < ITEMS; s++) {
+        if (!ok[s]) continue;
+        const float4 *c = src + p[s] * G + g;
+        const int lo = COLS ? a[s].x : a[s].z, hi = COLS ? a[s].y : a[s].w;     // (up, down) | (left, right)
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        cs_add(acc, stage[0][s][threadIdx.x]);                   // x, x-1, .., x-lo, then x+1, .., x+hi (pf:640-650)
+#pragma unroll
+        for (int k = 1; k <= NB; k++)
+            if (lo >= k) cs_add(acc, stage[2 * k - 1][s][threadIdx.x]);
+        for (int k = NB + 1; k <= lo; k++) cs_add(acc, c[-k * stride]);
+#pragma unroll
+        for (int k = 1; k <= NB; k++)
+            if (hi >= k) cs_add(acc, stage[2 * k][s][threadIdx.x]);
+        for (int k = NB + 1; k <= hi; k++) cs_add(acc, c[k * stride]);
+        if (COLS) {
+            const float vmax = fmaxf(fmaxf(fabsf(acc.x), fabsf(acc.y)), fmaxf(fabsf(acc.z), fabsf(acc.w)));
+            const float vmin = fminf(fminf(fabsf(acc.x), fabsf(acc.y)), fminf(fabsf(acc.z), fabsf(acc.w)));
+            if (vmax < 1e30f && vmin > 1e-30f) {
+                const float y = 1.0f / n[s];
+                acc = make_float4(cs_div1(acc.x, n[s], y), cs_div1(acc.y, n[s], y), cs_div1(acc.z, n[s], y), cs_div1(acc.w, n[s], y));
+            } else {
+                acc = make_float4(acc.x / n[s], acc.y / n[s], acc.z / n[s], acc.w / n[s]);   // pf:161
+            }
+        }
+        dst[p[s] * G + g] = acc;
     }
 }
 
