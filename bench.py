@@ -285,8 +285,6 @@ def run_ours(args):
         #  algorithmic figure is the fused minimum of 8 B/cell/round, the two passes actually move 16 B/cell)
         model = {
             "cbca2": (8.0 * cells_rank * it2 * 2, it2 * 2, "k_cbca_pass<rows>+k_cbca_pass<cols>"),
-            "sgm_rows": (8.0 * cells_rank * 2 * 2, 2, "k_sgm_pass"),
-            "sgm_cols": (8.0 * cells_rank * 2 * 2, 2, "k_sgm_pass"),
         } if slab else {
             "cost_volume": ((8.0 + 512.0 / D) * cells, 1, "k_cost_volume_tc (+k_cost_fill)"),
             "cbca1": (8.0 * cells * it1 * 2, it1 * 2, "k_cbca_pass<rows>+k_cbca_pass<cols>"),

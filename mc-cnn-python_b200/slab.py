@@ -3,7 +3,8 @@
 The reference has no such mode (its only parallelism is disjoint pair windows, match.py:26-28); the stage order
 and every per-cell result are those of match.py:131-175, only *where* a cell is computed changes:
 
-  features              replicated (0.6 MB of weights, the pair's two images)
+  features              row bands (each rank runs the net on its rows plus the 5-row halo of the receptive field),
+                        then every rank receives the other bands: the cost volume needs whole feature maps
   cost volume, CBCA     rank g owns disparities [d_base_g, d_base_g + d_count_g): independent per disparity plane
                         (pf:94-95 runs along w inside one d; cross regions ignore d)
   SGM                   needs all disparities of a pixel (pf:549-566): the volumes are re-partitioned
@@ -88,11 +89,19 @@ class LocalComm(object):
     def __init__(self, world):
         self.world = int(world)
 
-    def exchange(self, sends, recvs):
+    def exchange_begin(self, sends, recvs):
         """sends[i][j] = block rank i sends to rank j; recvs[j][i] = where rank j receives it."""
         for i in range(self.world):
             for j in range(self.world):
-                recvs[j][i].copy_(sends[i][j])
+                if recvs[j][i].data_ptr() != sends[i][j].data_ptr():
+                    recvs[j][i].copy_(sends[i][j])
+        return None
+
+    def exchange_end(self, handle):
+        pass
+
+    def exchange(self, sends, recvs):
+        self.exchange_end(self.exchange_begin(sends, recvs))
 
     def all_gather(self, parts):
         """parts[i] = rank i's tensor; returns per rank the stacked [world, ...] tensor."""
@@ -117,10 +126,14 @@ class DistComm(object):
         self.world = dist.get_world_size()
         self.rank = dist.get_rank()
 
-    def exchange(self, sends, recvs):
+    def exchange_begin(self, sends, recvs):
+        """Start the grouped send/recv (one ncclGroupStart/End: an all-to-all over NVLink); it runs on the
+        communicator's stream, after everything already queued on the current stream, and alongside what is
+        queued next -- exchange_end() makes the current stream wait for it."""
         dist = self.dist
         send, recv = sends[0], recvs[0]
-        recv[self.rank].copy_(send[self.rank])
+        if recv[self.rank].data_ptr() != send[self.rank].data_ptr():
+            recv[self.rank].copy_(send[self.rank])
         ops = []
         for j in range(self.world):
             if j != self.rank:
@@ -128,9 +141,14 @@ class DistComm(object):
         for j in range(self.world):
             if j != self.rank:
                 ops.append(dist.P2POp(dist.isend, send[j], j))
-        if ops:
-            for w in dist.batch_isend_irecv(ops):          # one ncclGroupStart/End: an all-to-all over NVLink
-                w.wait()
+        return dist.batch_isend_irecv(ops) if ops else []
+
+    def exchange_end(self, handle):
+        for w in handle:
+            w.wait()
+
+    def exchange(self, sends, recvs):
+        self.exchange_end(self.exchange_begin(sends, recvs))
 
     def all_gather(self, parts):
         import torch
@@ -186,8 +204,8 @@ class SlabRank(object):
         self.colv = [e(H, Wc, self.Dp), e(H, Wc, self.Dp)]
         # exchange staging: every re-partition moves exactly one slab's worth of cells out and in
         nstage = max(H * W * self.Dlp, Hr * W * self.Dp, H * Wc * self.Dp)
-        self.stage_out = e(nstage)
-        self.stage_in = e(nstage)
+        self.stage_out = [e(nstage), e(nstage)]            # per volume: the two volumes' exchanges are in flight together
+        self.stage_in = [e(nstage), e(nstage)]
         self.arms = [e(H, W, 4, dtype=torch.uint8), e(H, W, 4, dtype=torch.uint8)]
         self.count = [e(H, W, dtype=torch.int32), e(H, W, dtype=torch.int32)]
         self.cbca_ws = _pf.cbca_workspace(H, W)
@@ -207,25 +225,39 @@ class SlabRank(object):
             self.img[i].copy_(_pf._image2d(im))
 
     # ---- phases --------------------------------------------------------------------------------
+    def features_band(self):
+        """Features of this rank's rows (match.py:132): the net sees 5 rows beyond the band on either side (its
+        receptive field is 11), so rows [h0 - 5, h1 + 5) are run and only [h0, h1) are kept -- the rest arrives from
+        the ranks that own it."""
+        p, call, sp, pl = _ffi.ptr, _ffi.call, _ffi.stream_ptr, self.plan
+        a, b = max(0, self.h0 - self.pad), min(pl.H, self.h1 + self.pad)
+        for i in range(2):
+            call("mccnn_features", ctypes.c_void_p(self.img[i].data_ptr() + 4 * a * pl.W), b - a, pl.W, self.pad, self.pad,
+                 self.weights.w_table, self.weights.b_table, ctypes.c_void_p(self.feat[i].data_ptr() + 4 * a * pl.W * 64),
+                 p(self.feat_scratch), sp())
+
+    def send_features(self, i):
+        return [self.feat[i][self.h0:self.h1] for _ in range(self.plan.world)]
+
+    def recv_features(self, i):
+        return [self.feat[i][lo:hi] for lo, hi in self.plan.rows]
+
     def front(self):
-        """features, this slab of the cost volume, cross arms, CBCA x iters1 (match.py:132-143)."""
+        """This slab of the cost volume, cross arms, CBCA x iters1 (match.py:137-143)."""
         p, call, sp, hp, pl = _ffi.ptr, _ffi.call, _ffi.stream_ptr, self.hp, self.plan
         H, W, D = pl.H, pl.W, pl.D
-        for i in range(2):
-            call("mccnn_features", p(self.img[i]), H, W, self.pad, self.pad, self.weights.w_table, self.weights.b_table,
-                 p(self.feat[i]), p(self.feat_scratch), sp())
         call("mccnn_cost_volume_slab", p(self.feat[0]), p(self.feat[1]), p(self.volA[0]), p(self.volA[1]), H, W, 64, D,
              self.dbase, self.Dl, sp())
         for i in range(2):
             call("mccnn_cross_arms", p(self.img[i]), p(self.arms[i]), p(self.count[i]), H, W,
                  ctypes.c_float(np.float32(hp["cbca_intensity"])), int(hp["cbca_distance"]), sp())
-        self._cbca(self.volA, self.volB, int(hp["cbca_num_iterations1"]))
+        for v in range(2):
+            self._cbca(v, self.volA, self.volB, int(hp["cbca_num_iterations1"]))
 
-    def _cbca(self, src, dst, iters):
+    def _cbca(self, i, src, dst, iters):
         p, call, sp, hp, pl = _ffi.ptr, _ffi.call, _ffi.stream_ptr, self.hp, self.plan
-        for i in range(2):
-            call("mccnn_cbca", p(src[i]), p(dst[i]), p(self.volS), p(self.arms[i]), p(self.count[i]), self.Dl, pl.H, pl.W,
-                 iters, int(hp["cbca_distance"]), int(self.cbca_mode), p(self.cbca_ws), sp())
+        call("mccnn_cbca", p(src[i]), p(dst[i]), p(self.volS), p(self.arms[i]), p(self.count[i]), self.Dl, pl.H, pl.W,
+             iters, int(hp["cbca_distance"]), int(self.cbca_mode), p(self.cbca_ws), sp())
 
     def _views(self, flat, shapes):
         out, off = [], 0
@@ -242,7 +274,7 @@ class SlabRank(object):
     def recv_rows(self, v):
         pl = self.plan
         Hr = self.h1 - self.h0
-        return self._views(self.stage_in, [(Hr, pl.W, 4 * pl.g_count(j)) for j in range(pl.world)])
+        return self._views(self.stage_in[v], [(Hr, pl.W, 4 * pl.g_count(j)) for j in range(pl.world)])
 
     def unpack_rows(self, v, blocks):
         pl = self.plan
@@ -251,21 +283,21 @@ class SlabRank(object):
             gj = pl.g_count(j)
             _copy3d(blk, 0, self.rowv[v], pl.granules[j][0], 1, n, gj, 0, gj, 0, pl.G)
 
-    def sgm_rows(self):
-        """(0,1) then (0,-1), pf:195-198, on rows [h0, h1)."""
+    def sgm_rows(self, v):
+        """(0,1) then (0,-1), pf:195-198, on rows [h0, h1) of volume v (0 left, 1 right)."""
         p, call, sp, hp, pl = _ffi.ptr, _ffi.call, _ffi.stream_ptr, self.hp, self.plan
         off = 4 * self.h0 * pl.W
         il = ctypes.c_void_p(self.img[0].data_ptr() + off)
         ir = ctypes.c_void_p(self.img[1].data_ptr() + off)
-        call("mccnn_sgm_passes_slab", p(self.rowv[0]), p(self.rowv[1]), il, ir, p(self.sgm_flags), pl.D,
-             self.h1 - self.h0, pl.W, 0, pl.W, 0, float(hp["sgm_P1"]), float(hp["sgm_P2"]), float(hp["sgm_Q1"]),
-             float(hp["sgm_Q2"]), float(hp["sgm_D"]), float(hp["sgm_V"]), sp())
+        call("mccnn_sgm_passes_slab", p(self.rowv[0]) if v == 0 else None, p(self.rowv[1]) if v == 1 else None, il, ir,
+             p(self.sgm_flags), pl.D, self.h1 - self.h0, pl.W, 0, pl.W, 0, float(hp["sgm_P1"]), float(hp["sgm_P2"]),
+             float(hp["sgm_Q1"]), float(hp["sgm_Q2"]), float(hp["sgm_D"]), float(hp["sgm_V"]), sp())
 
     # row slabs -> column slabs: block for rank j = its columns of my rows (packed), lands as rows of its slab
     def send_cols(self, v):
         pl = self.plan
         Hr = self.h1 - self.h0
-        views = self._views(self.stage_out, [(Hr, pl.w_count(j), self.Dp) for j in range(pl.world)])
+        views = self._views(self.stage_out[v], [(Hr, pl.w_count(j), self.Dp) for j in range(pl.world)])
         for j, blk in enumerate(views):
             wj = pl.w_count(j)
             _copy3d(self.rowv[v], pl.cols[j][0] * pl.G, blk, 0, Hr, wj, pl.G, pl.W * pl.G, pl.G, wj * pl.G, pl.G)
@@ -274,18 +306,19 @@ class SlabRank(object):
     def recv_cols(self, v):
         return [self.colv[v][lo:hi] for lo, hi in self.plan.rows]
 
-    def sgm_cols(self):
-        """(-1,0) then (1,0), pf:203-208, on columns [w0, w1)."""
+    def sgm_cols(self, v):
+        """(-1,0) then (1,0), pf:203-208, on columns [w0, w1) of volume v."""
         p, call, sp, hp, pl = _ffi.ptr, _ffi.call, _ffi.stream_ptr, self.hp, self.plan
-        call("mccnn_sgm_passes_slab", p(self.colv[0]), p(self.colv[1]), p(self.img[0]), p(self.img[1]), p(self.sgm_flags),
-             pl.D, pl.H, pl.W, self.w0, self.w1 - self.w0, 1, float(hp["sgm_P1"]), float(hp["sgm_P2"]),
-             float(hp["sgm_Q1"]), float(hp["sgm_Q2"]), float(hp["sgm_D"]), float(hp["sgm_V"]), sp())
+        call("mccnn_sgm_passes_slab", p(self.colv[0]) if v == 0 else None, p(self.colv[1]) if v == 1 else None,
+             p(self.img[0]), p(self.img[1]), p(self.sgm_flags), pl.D, pl.H, pl.W, self.w0, self.w1 - self.w0, 1,
+             float(hp["sgm_P1"]), float(hp["sgm_P2"]), float(hp["sgm_Q1"]), float(hp["sgm_Q2"]), float(hp["sgm_D"]),
+             float(hp["sgm_V"]), sp())
 
     # column slabs -> d-slabs: block for rank j = its disparities of my columns (packed); unpacked into columns
     def send_slabs(self, v):
         pl = self.plan
         Wc = self.w1 - self.w0
-        views = self._views(self.stage_out, [(pl.H, Wc, 4 * pl.g_count(j)) for j in range(pl.world)])
+        views = self._views(self.stage_out[v], [(pl.H, Wc, 4 * pl.g_count(j)) for j in range(pl.world)])
         for j, blk in enumerate(views):
             gj = pl.g_count(j)
             _copy3d(self.colv[v], pl.granules[j][0], blk, 0, 1, pl.H * Wc, gj, 0, pl.G, 0, gj)
@@ -293,7 +326,7 @@ class SlabRank(object):
 
     def recv_slabs(self, v):
         pl = self.plan
-        return self._views(self.stage_in, [(pl.H, pl.w_count(j), self.Dlp) for j in range(pl.world)])
+        return self._views(self.stage_in[v], [(pl.H, pl.w_count(j), self.Dlp) for j in range(pl.world)])
 
     def unpack_slabs(self, v, blocks):
         pl = self.plan
@@ -302,9 +335,9 @@ class SlabRank(object):
             wj = pl.w_count(j)
             _copy3d(blk, 0, self.volB[v], pl.cols[j][0] * gl, pl.H, wj, gl, wj * gl, gl, pl.W * gl, gl)
 
-    def cbca2(self):
-        """CBCA x iters2 (match.py:154-155)."""
-        self._cbca(self.volB, self.volA, int(self.hp["cbca_num_iterations2"]))
+    def cbca2(self, v):
+        """CBCA x iters2 of volume v (match.py:154-155)."""
+        self._cbca(v, self.volB, self.volA, int(self.hp["cbca_num_iterations2"]))
 
     def wta(self):
         """This slab's winners and their costs (match.py:159)."""
@@ -349,35 +382,43 @@ def run_slabs(ranks, comm, marks=None):
             ev.record()
             marks.append((name, ev))
 
+    # The two volumes are independent until WTA: the exchange of one runs under the passes of the other.
+    begin, end = comm.exchange_begin, comm.exchange_end
     mark("start")
+    for r in ranks:
+        r.features_band()
+    if ranks[0].plan.world > 1:
+        hf = [begin([r.send_features(i) for r in ranks], [r.recv_features(i) for r in ranks]) for i in range(2)]
+        for h in hf:
+            end(h)
+    mark("features")
     for r in ranks:
         r.front()
     mark("front")
+    recv_rows = [[r.recv_rows(v) for r in ranks] for v in range(2)]
+    h_rows = [begin([r.send_rows(v) for r in ranks], recv_rows[v]) for v in range(2)]
+    h_cols, h_slabs = [None, None], [None, None]
     for v in range(2):
-        sends = [r.send_rows(v) for r in ranks]
-        recvs = [r.recv_rows(v) for r in ranks]
-        comm.exchange(sends, recvs)
-        for r, blocks in zip(ranks, recvs):
+        end(h_rows[v])
+        for r, blocks in zip(ranks, recv_rows[v]):
             r.unpack_rows(v, blocks)
-    mark("to_rows")
-    for r in ranks:
-        r.sgm_rows()
-    mark("sgm_rows")
+        for r in ranks:
+            r.sgm_rows(v)
+        h_cols[v] = begin([r.send_cols(v) for r in ranks], [r.recv_cols(v) for r in ranks])
+    recv_slabs = [None, None]
     for v in range(2):
-        comm.exchange([r.send_cols(v) for r in ranks], [r.recv_cols(v) for r in ranks])
-    mark("to_cols")
-    for r in ranks:
-        r.sgm_cols()
-    mark("sgm_cols")
+        end(h_cols[v])
+        for r in ranks:
+            r.sgm_cols(v)
+        recv_slabs[v] = [r.recv_slabs(v) for r in ranks]
+        h_slabs[v] = begin([r.send_slabs(v) for r in ranks], recv_slabs[v])
+    mark("sgm_and_exchanges")
     for v in range(2):
-        sends = [r.send_slabs(v) for r in ranks]
-        recvs = [r.recv_slabs(v) for r in ranks]
-        comm.exchange(sends, recvs)
-        for r, blocks in zip(ranks, recvs):
+        end(h_slabs[v])
+        for r, blocks in zip(ranks, recv_slabs[v]):
             r.unpack_slabs(v, blocks)
-    mark("to_slabs")
-    for r in ranks:
-        r.cbca2()
+        for r in ranks:
+            r.cbca2(v)
     mark("cbca2")
     gathered = comm.all_gather([r.wta() for r in ranks])
     comm.all_reduce_sum([r.combine(g) for r, g in zip(ranks, gathered)])

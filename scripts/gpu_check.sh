@@ -24,9 +24,9 @@ for a in "$@"; do
   fi
   if [ "$a" = "full" ]; then
     echo "== ncu full captures"
-    for k in k_cbca_round_sep k_sgm_pass k_cost_volume k_conv64 k_wta; do
+    for k in k_cbca_pass k_sgm_pass k_cost_volume_tc k_conv64_tc k_wta; do
       timeout 900 ncu --set full --clock-control none --import-source on -k regex:$k -s 4 -c 2 \
-          -o gpurun_out/prof_$k -f python scripts/profile_step.py 2 > gpurun_out/ncu_$k.log 2>&1
+          -o gpurun_out/r1z_$k -f python scripts/profile_step.py 2 > gpurun_out/ncu_$k.log 2>&1
       tail -1 gpurun_out/ncu_$k.log
     done
   fi
