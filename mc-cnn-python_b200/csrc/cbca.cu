@@ -209,7 +209,7 @@ static int launch_march(const CmMaps &maps, float *dst, const uint8_t *arms, con
 // One round of the default mode: row sums src -> scratch, column sums scratch -> out.
 static int stream_round(const float *src, float *scratch, float *out, const uint8_t *arms, const int32_t *count, int G, int H,
                         int W, cudaStream_t s) {
-    dim3 grid(cdiv(W, CS_PW) * cdiv(G, CS_GC), cdiv(H, CS_PH));
+    dim3 grid(cdiv(G, CS_GC), cdiv(W, CS_PW), cdiv(H, CS_PH));
     k_cbca_pass<false, CS_ITEMS, 1><<<grid, CS_THREADS, 0, s>>>(reinterpret_cast<const float4 *>(src), reinterpret_cast<float4 *>(scratch),
                                                                 reinterpret_cast<const uchar4 *>(arms), count, G, H, W);
     MCCNN_LAUNCHED("cbca_rows");

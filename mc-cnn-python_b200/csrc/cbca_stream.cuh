@@ -50,9 +50,10 @@ __global__ void __launch_bounds__(CS_THREADS, CS_MIN_BLOCKS) k_cbca_pass(const f
                                                           int G, int H, int W) {
     __shared__ float4 stage[2 * NB + 1][ITEMS][CS_THREADS];      // [centre, -1, +1, -2, +2, ..]
     constexpr int PH = 2 * ITEMS;
-    // the granule groups of a patch are consecutive CTAs (a pixel's 4*Dp bytes are fetched together: DRAM pages)
-    const int nz = (G + CS_GC - 1) / CS_GC, bx = blockIdx.x / nz, bz = blockIdx.x - bx * nz;
-    const int gi = threadIdx.x % CS_GC, g = bz * CS_GC + gi;
+    // grid = (granule groups, patch columns, patch rows): the granule groups of a patch are consecutive CTAs, so a
+    // pixel's 4*Dp bytes are fetched together (DRAM pages)
+    const int bx = blockIdx.y, by = blockIdx.z;
+    const int gi = threadIdx.x % CS_GC, g = blockIdx.x * CS_GC + gi;
     if (g >= G) return;
     const ptrdiff_t stride = COLS ? (ptrdiff_t)W * G : (ptrdiff_t)G;
     size_t p[ITEMS];
@@ -62,7 +63,7 @@ __global__ void __launch_bounds__(CS_THREADS, CS_MIN_BLOCKS) k_cbca_pass(const f
 #pragma unroll
     for (int s = 0; s < ITEMS; s++) {
         const int pi = s * (CS_THREADS / CS_GC) + threadIdx.x / CS_GC;
-        const int h = blockIdx.y * PH + pi / CS_PW, w = bx * CS_PW + pi % CS_PW;
+        const int h = by * PH + pi / CS_PW, w = bx * CS_PW + pi % CS_PW;
         ok[s] = h < H && w < W;
         p[s] = ok[s] ? (size_t)h * W + w : 0;
         if (ok[s]) {
