@@ -158,6 +158,17 @@ int mccnn_sgm_passes_slab(float *vol_left, float *vol_right, const float *img_le
                           double sgm_P1, double sgm_P2, double sgm_Q1, double sgm_Q2, double sgm_D,
                           double sgm_V, void *stream);
 
+/* The same with the pair's second pass storing every cell straight into the buffer of the rank that needs it in
+ * the next layout (peer memory over NVLink) instead of in place: which = 0 sends columns [bounds[r], bounds[r+1])
+ * to dst_*[r], a column slab [H_total][bounds[r+1]-bounds[r]][Dp] whose row h_base + h receives this slab's row h;
+ * which = 1 sends granules [bounds[r], bounds[r+1]) to dst_*[r], a disparity slab [H][W][4*(bounds[r+1]-bounds[r])].
+ * bounds (nparts + 1 ints) and the dst tables (nparts device pointers each) are HOST arrays; nparts <= 8. */
+int mccnn_sgm_passes_slab_to(float *vol_left, float *vol_right, const float *img_left, const float *img_right,
+                             void *flags_scratch, int D, int H, int W, int w_base, int w_count, int which,
+                             double sgm_P1, double sgm_P2, double sgm_Q1, double sgm_Q2, double sgm_D,
+                             double sgm_V, int nparts, const int *bounds, float *const *dst_left,
+                             float *const *dst_right, int h_base, void *stream);
+
 /* a8 on a slab of D disparities starting at d_base: disp = the pair's disparity of the slab's first minimum,
  * minval = its cost.  mccnn_wta_combine takes the all-gathered arrays (slab s at element s * slab_stride) and keeps, per pixel, the
  * first strict minimum in slab order (the lowest disparity wins ties, pf:247-252). */

@@ -12,4 +12,4 @@ from . import pipeline                  # noqa: F401
 from .model import NET                  # noqa: F401
 from .pipeline import StereoMatcher, match_pair, shard_window, DEFAULTS   # noqa: F401
 from . import slab                      # noqa: F401
-from .slab import SlabPlan, SlabRank, SlabMatcher, LocalComm, DistComm, run_slabs   # noqa: F401
+from .slab import SlabPlan, SlabRank, SlabMatcher, LocalComm, DistComm, run_slabs, run_slabs_p2p   # noqa: F401

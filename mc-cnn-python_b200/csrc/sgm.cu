@@ -25,8 +25,24 @@ struct SgmJob {
     int is_left;
 };
 
+// Where a pass stores its result when the volume is about to be re-partitioned (one big pair over several GPUs):
+// instead of writing in place and packing / sending / unpacking afterwards, the pass writes every cell straight
+// into the buffer of the rank that needs it next, over NVLink peer memory.
+//   mode 1 (horizontal pass on a ROW slab): pixel (h, w) goes to the rank that owns column w, into its column
+//           slab [H][w_count_r][Dp] at row h_base + h;
+//   mode 2 (vertical pass on a COLUMN slab): granule g of pixel (h, w) goes to the rank that owns granule g, into
+//           its disparity slab [H][W][4 * g_count_r] at column w_base + w.
+constexpr int SGM_MAX_PARTS = 8;
+struct SgmScatter {
+    int mode, nparts;
+    int lo[SGM_MAX_PARTS + 1];               // column (mode 1) or granule (mode 2) bounds of the parts
+    float4 *base[2][SGM_MAX_PARTS];          // [job][part]: the destination buffers
+    int h_base, w_full;                      // mode 1: global row of this slab's row 0; mode 2: image width
+};
+
 struct SgmParams {
     SgmJob job[2];
+    SgmScatter sc;
     int D, G, NLg, H, W, WR, PADW;   // W = width of the volume (and of the images unless wbase/flag geometry say otherwise)
     int wbase;                       // image column of the volume's column 0 (column slabs of one big pair)
     int rh, rw;
@@ -73,7 +89,7 @@ __device__ __forceinline__ void sgm_cp_async16(void *smem_dst, const void *gmem_
 // (cells are fetched CP - 1 steps ahead with cp.async: the pass is bound by bytes in flight -- there are only H or
 // W scanlines x 2 volumes = 2048 warps on the whole chip -- and a ring in shared memory buys look-ahead that
 // registers cannot).
-template <int JP, int PF, int CP>
+template <int JP, int PF, int CP, bool SC = false>
 __global__ void __launch_bounds__(32, 16) k_sgm_pass(const __grid_constant__ SgmParams prm) {
     __shared__ float4 cring[CP][JP][32];
     constexpr int DIST = CP - 1;
@@ -100,6 +116,35 @@ __global__ void __launch_bounds__(32, 16) k_sgm_pass(const __grid_constant__ Sgm
     const int src_dn = (lane == 0) ? NLg - 1 : lane - 1;
     const int src_up = (lane >= NLg - 1) ? 0 : lane + 1;
     const bool first_lane = (lane == 0), last_lane = (lane == NLg - 1);
+
+    // scatter destinations (SC): mode 2 is fixed per lane granule for the whole pass, mode 1 changes with the pixel
+    float4 *sc_dst[JP];                      // mode 2: destination of granule g[j] at pixel 0 of its slab
+    int sc_pitch[JP];                        //         granules per pixel of that slab
+    if (SC && prm.sc.mode == 2) {
+#pragma unroll
+        for (int j = 0; j < JP; j++) {
+            sc_dst[j] = nullptr; sc_pitch[j] = 0;
+            if (gv[j]) {
+                int r = 0;
+                while (r + 1 < prm.sc.nparts && g[j] >= prm.sc.lo[r + 1]) r++;
+                sc_pitch[j] = prm.sc.lo[r + 1] - prm.sc.lo[r];
+                sc_dst[j] = prm.sc.base[blockIdx.y][r] + (g[j] - prm.sc.lo[r]);
+            }
+        }
+    }
+    // cell (pixel index p of this slab = h * W + w, lane granule j) -> where it is stored
+    auto store_cell = [&](long long p, int t, int j, const float4 &v) {
+        if (!SC) { vol4[p * G + g[j]] = v; return; }
+        const int h = h0 + t * dh, w = w0 + t * dw;              // pixel of step t on this scanline
+        if (prm.sc.mode == 1) {
+            int r = 0;
+            while (r + 1 < prm.sc.nparts && w >= prm.sc.lo[r + 1]) r++;
+            const int wc = prm.sc.lo[r + 1] - prm.sc.lo[r];
+            prm.sc.base[blockIdx.y][r][((size_t)(prm.sc.h_base + h) * wc + (w - prm.sc.lo[r])) * G + g[j]] = v;
+        } else {
+            sc_dst[j][((size_t)h * prm.sc.w_full + prm.wbase + w) * sc_pitch[j]] = v;
+        }
+    };
 
     auto fix_ragged = [&](float4 &v, int j) {
         if (ragged) {
@@ -180,6 +225,7 @@ __global__ void __launch_bounds__(32, 16) k_sgm_pass(const __grid_constant__ Sgm
                 fix_ragged(v, j);
             }
             prev[j] = v;
+            if (SC && gv[j]) store_cell(p0, 0, j, v);               // (the seed pixel travels unchanged)
         }
     }
 #pragma unroll 1
@@ -234,7 +280,7 @@ __global__ void __launch_bounds__(32, 16) k_sgm_pass(const __grid_constant__ Sgm
                     o.y = (cur[j].y + fminf(q.y, fminf(fminf(q.x, q.z) + ((b & 2u) ? pb1 : pa1), (b & 2u) ? cB : cA))) - m;
                     o.z = (cur[j].z + fminf(q.z, fminf(fminf(q.y, q.w) + ((b & 4u) ? pb1 : pa1), (b & 4u) ? cB : cA))) - m;
                     o.w = (cur[j].w + fminf(q.w, fminf(fminf(q.z, rnb) + ((b & 8u) ? pb1 : pa1), (b & 8u) ? cB : cA))) - m;
-                    if (gv[j]) vol4[p * G + g[j]] = o;
+                    if (gv[j]) store_cell(p, t, j, o);
                     prev[j] = o;
                     lm = fminf(fminf(lm, fminf(o.x, o.y)), fminf(o.z, o.w));
                 }
@@ -248,6 +294,18 @@ static int launch_pass(const SgmParams &prm, int njobs, cudaStream_t s) {
     const int JP = cdiv(prm.G, 32);
     const bool horizontal = (prm.rh == 0);
     dim3 grid(horizontal ? prm.H : prm.W, njobs), block(32);
+    if (prm.sc.mode != 0) {
+        switch (JP) {
+            case 1: k_sgm_pass<1, 4, 16, true><<<grid, block, 0, s>>>(prm); break;
+            case 2: k_sgm_pass<2, 4, 12, true><<<grid, block, 0, s>>>(prm); break;
+            case 3: k_sgm_pass<3, 3, 8, true><<<grid, block, 0, s>>>(prm); break;
+            case 4: k_sgm_pass<4, 2, 8, true><<<grid, block, 0, s>>>(prm); break;
+            default:
+                set_error("sgm: ndisp %d too large (max 512)", prm.D);
+                return MCCNN_ERR_UNSUPPORTED;
+        }
+        return check_launch("sgm_pass_scatter");
+    }
     switch (JP) {
         case 1: k_sgm_pass<1, 4, 16><<<grid, block, 0, s>>>(prm); break;
         case 2: k_sgm_pass<2, 4, 12><<<grid, block, 0, s>>>(prm); break;
@@ -284,6 +342,7 @@ static int check_dir(int rh, int rw) {
 static void fill_params(SgmParams &prm, int D, int H, int W, int rh, int rw, double P1, double P2, double Q1, double Q2) {
     SgmGeom gm = sgm_geom(H, W, D);
     prm.D = D; prm.G = dpitch(D) / 4; prm.H = H; prm.W = W; prm.WR = gm.WR; prm.PADW = gm.PADW; prm.wbase = 0;
+    prm.sc.mode = 0; prm.sc.nparts = 0;
     prm.NLg = cdiv(prm.G, cdiv(prm.G, 32));
     prm.rh = rh; prm.rw = rw;
     // float32 rounding exactly as pf:504-505 (P*ones(float32)) and pf:538-541 (float32 array / scalar)
@@ -364,9 +423,10 @@ int mccnn_sgm_average_pair(float *vol_left, float *vol_right, const float *img_l
 // ROW slab (volumes [h_count][W][Dp], images passed from their row h_base: rows are independent for horizontal
 // passes), which = 1 runs (-1,0) then (1,0) on a COLUMN slab (volumes [H][w_count][Dp] holding image columns
 // [w_base, w_base + w_count), full images: the penalty tests look up the other image at column w -/+ d).
-int mccnn_sgm_passes_slab(float *vol_left, float *vol_right, const float *img_left, const float *img_right,
-                          void *flags_scratch, int D, int H, int W, int w_base, int w_count, int which, double P1,
-                          double P2, double Q1, double Q2, double tauD, double V, void *stream) {
+static int sgm_passes_slab(float *vol_left, float *vol_right, const float *img_left, const float *img_right,
+                           void *flags_scratch, int D, int H, int W, int w_base, int w_count, int which, double P1,
+                           double P2, double Q1, double Q2, double tauD, double V, int nparts, const int *bounds,
+                           float *const *dst_left, float *const *dst_right, int h_base, void *stream) {
     MCCNN_REQUIRE((vol_left || vol_right) && img_left && img_right && flags_scratch, "sgm_passes_slab: null pointer");
     MCCNN_REQUIRE(D >= 2 && H >= 1 && W >= 1, "sgm_passes_slab: need ndisp >= 2, got D=%d H=%d W=%d", D, H, W);
     MCCNN_REQUIRE(w_base >= 0 && w_count >= 1 && w_base + w_count <= W, "sgm_passes_slab: columns [%d, %d) outside the image",
@@ -389,10 +449,51 @@ int mccnn_sgm_passes_slab(float *vol_left, float *vol_right, const float *img_le
         if (vol_left) fill_job(prm.job[n++], vol_left, maps, H, W, D, rh, 1);
         if (vol_right) fill_job(prm.job[n++], vol_right, maps, H, W, D, rh, 0);
         if (n == 1) prm.job[1] = prm.job[0];
+        if (i == 1 && nparts > 0) {                                              // the pair's last pass stores remotely
+            prm.sc.mode = which == 0 ? 1 : 2;
+            prm.sc.nparts = nparts;
+            for (int r = 0; r <= nparts; r++) prm.sc.lo[r] = bounds[r];
+            for (int r = 0; r < nparts; r++) {
+                int m = 0;
+                if (vol_left) prm.sc.base[m++][r] = reinterpret_cast<float4 *>(dst_left[r]);
+                if (vol_right) prm.sc.base[m++][r] = reinterpret_cast<float4 *>(dst_right[r]);
+                if (m == 1) prm.sc.base[1][r] = prm.sc.base[0][r];
+            }
+            prm.sc.h_base = h_base;
+            prm.sc.w_full = W;
+        }
         rc = launch_pass(prm, n, s);
         if (rc) return rc;
     }
     return MCCNN_OK;
+}
+
+int mccnn_sgm_passes_slab(float *vol_left, float *vol_right, const float *img_left, const float *img_right,
+                          void *flags_scratch, int D, int H, int W, int w_base, int w_count, int which, double P1,
+                          double P2, double Q1, double Q2, double tauD, double V, void *stream) {
+    return sgm_passes_slab(vol_left, vol_right, img_left, img_right, flags_scratch, D, H, W, w_base, w_count, which, P1, P2,
+                           Q1, Q2, tauD, V, 0, nullptr, nullptr, nullptr, 0, stream);
+}
+
+// The same, with the second pass of the pair storing every cell straight into the buffer of the rank that owns it
+// in the next layout (peer memory over NVLink; see SgmScatter): which = 0 sends columns [bounds[r], bounds[r+1]) to
+// dst_*[r], a column slab [h_total][bounds[r+1] - bounds[r]][Dp] whose row h_base + h receives this slab's row h;
+// which = 1 sends granules [bounds[r], bounds[r+1]) to dst_*[r], a disparity slab [H][W][4 * (bounds[r+1] - bounds[r])].
+// bounds and the dst tables are host arrays.
+int mccnn_sgm_passes_slab_to(float *vol_left, float *vol_right, const float *img_left, const float *img_right,
+                             void *flags_scratch, int D, int H, int W, int w_base, int w_count, int which, double P1,
+                             double P2, double Q1, double Q2, double tauD, double V, int nparts, const int *bounds,
+                             float *const *dst_left, float *const *dst_right, int h_base, void *stream) {
+    MCCNN_REQUIRE(nparts >= 1 && nparts <= SGM_MAX_PARTS && bounds, "sgm_passes_slab_to: 1 to %d parts", SGM_MAX_PARTS);
+    MCCNN_REQUIRE((!vol_left || dst_left) && (!vol_right || dst_right), "sgm_passes_slab_to: destination table missing");
+    const int extent = which == 0 ? W : dpitch(D) / 4;
+    MCCNN_REQUIRE(bounds[0] == 0 && bounds[nparts] == extent, "sgm_passes_slab_to: bounds must tile [0, %d)", extent);
+    for (int r = 0; r < nparts; r++) {
+        MCCNN_REQUIRE(bounds[r] < bounds[r + 1], "sgm_passes_slab_to: empty part %d", r);
+        MCCNN_REQUIRE((!vol_left || dst_left[r]) && (!vol_right || dst_right[r]), "sgm_passes_slab_to: null destination %d", r);
+    }
+    return sgm_passes_slab(vol_left, vol_right, img_left, img_right, flags_scratch, D, H, W, w_base, w_count, which, P1, P2,
+                           Q1, Q2, tauD, V, nparts, bounds, dst_left, dst_right, h_base, stream);
 }
 
 int mccnn_sgm_average(float *vol, const float *img_left, const float *img_right, void *flags_scratch, int D, int H,

@@ -75,6 +75,13 @@ class SlabPlan(object):
     def w_count(self, r):
         return self.cols[r][1] - self.cols[r][0]
 
+    def region_floats(self):
+        """Floats of the largest d-slab / row-slab / column-slab volume any rank holds (the size of one region of
+        the symmetric arena: identical on every rank, as peer memory requires)."""
+        Dp = 4 * self.G
+        return max(max(self.H * self.W * 4 * self.g_count(r), self.h_count(r) * self.W * Dp, self.H * self.w_count(r) * Dp)
+                   for r in range(self.world))
+
     def owner_of_disparity(self, d):
         for r in range(self.world):
             if self.d_base(r) <= d < self.d_base(r) + self.d_count(r):
@@ -102,6 +109,18 @@ class LocalComm(object):
 
     def exchange(self, sends, recvs):
         self.exchange_end(self.exchange_begin(sends, recvs))
+
+    def make_arenas(self, nfloats):
+        """One arena per rank for the volumes peers write into (here: ordinary device memory of the one GPU)."""
+        torch = _pf._torch()
+        self.arenas = [torch.empty(int(nfloats), dtype=torch.float32, device=_pf._dev()) for _ in range(self.world)]
+        return self.arenas
+
+    def peer_bases(self, local_index):
+        return [a.data_ptr() for a in self.arenas]
+
+    def barrier(self):
+        pass
 
     def all_gather(self, parts):
         """parts[i] = rank i's tensor; returns per rank the stacked [world, ...] tensor."""
@@ -150,6 +169,21 @@ class DistComm(object):
     def exchange(self, sends, recvs):
         self.exchange_end(self.exchange_begin(sends, recvs))
 
+    def make_arenas(self, nfloats):
+        """The arena peers write into: symmetric memory (same size on every rank), mapped into every rank's address
+        space over NVLink by the rendezvous."""
+        import torch
+        import torch.distributed._symmetric_memory as symm_mem
+        self.arena = symm_mem.empty(int(nfloats), dtype=torch.float32, device=torch.device("cuda", torch.cuda.current_device()))
+        self.symm = symm_mem.rendezvous(self.arena, self.dist.group.WORLD)
+        return [self.arena]
+
+    def peer_bases(self, local_index):
+        return [int(p) for p in self.symm.buffer_ptrs]
+
+    def barrier(self):
+        self.symm.barrier()                          # device-side, on the current stream
+
     def all_gather(self, parts):
         import torch
         t = parts[0].contiguous()
@@ -172,7 +206,7 @@ def _copy3d(src, src_off, dst, dst_off, n0, n1, n2, ss0, ss1, ds0, ds1):
 class SlabRank(object):
     """Buffers and C-ABI calls of one rank of the partition."""
 
-    def __init__(self, plan, rank, checkpoint=None, cbca_mode=None, **hp):
+    def __init__(self, plan, rank, checkpoint=None, cbca_mode=None, arena=None, **hp):
         torch = _pf._torch()
         self.torch = torch
         self.plan, self.rank = plan, int(rank)
@@ -197,15 +231,24 @@ class SlabRank(object):
         self.feat_scratch = e((nb + 3) // 4)
         # d-slab volumes (A: cost volume / CBCA2 output, B: CBCA1 output and SGM result, S: CBCA scratch)
         self.volA = [e(H, W, self.Dlp), e(H, W, self.Dlp)]
-        self.volB = [e(H, W, self.Dlp), e(H, W, self.Dlp)]
         self.volS = e(H, W, self.Dlp)
-        # the same cells as row slabs (all disparities of rows [h0, h1)) and column slabs (columns [w0, w1))
-        self.rowv = [e(Hr, W, self.Dp), e(Hr, W, self.Dp)]
-        self.colv = [e(H, Wc, self.Dp), e(H, Wc, self.Dp)]
-        # exchange staging: every re-partition moves exactly one slab's worth of cells out and in
-        nstage = max(H * W * self.Dlp, Hr * W * self.Dp, H * Wc * self.Dp)
-        self.stage_out = [e(nstage), e(nstage)]            # per volume: the two volumes' exchanges are in flight together
-        self.stage_in = [e(nstage), e(nstage)]
+        # B and the same cells as row slabs (all disparities of rows [h0, h1)) and column slabs (columns [w0, w1)):
+        # either private buffers filled through staged exchanges, or six regions of an arena that peers write into
+        # directly (region k of every rank's arena starts at k * plan.region_floats())
+        self.region = plan.region_floats()
+        if arena is None:
+            self.volB = [e(H, W, self.Dlp), e(H, W, self.Dlp)]
+            self.rowv = [e(Hr, W, self.Dp), e(Hr, W, self.Dp)]
+            self.colv = [e(H, Wc, self.Dp), e(H, Wc, self.Dp)]
+            # exchange staging: every re-partition moves exactly one slab's worth of cells out and in
+            nstage = max(H * W * self.Dlp, Hr * W * self.Dp, H * Wc * self.Dp)
+            self.stage_out = [e(nstage), e(nstage)]        # per volume: the two volumes' exchanges are in flight together
+            self.stage_in = [e(nstage), e(nstage)]
+        else:
+            reg = lambda k, *shape: arena[k * self.region:k * self.region + int(np.prod(shape))].view(*shape)
+            self.volB = [reg(0, H, W, self.Dlp), reg(1, H, W, self.Dlp)]
+            self.rowv = [reg(2, Hr, W, self.Dp), reg(3, Hr, W, self.Dp)]
+            self.colv = [reg(4, H, Wc, self.Dp), reg(5, H, Wc, self.Dp)]
         self.arms = [e(H, W, 4, dtype=torch.uint8), e(H, W, 4, dtype=torch.uint8)]
         self.count = [e(H, W, dtype=torch.int32), e(H, W, dtype=torch.int32)]
         self.cbca_ws = _pf.cbca_workspace(H, W)
@@ -335,6 +378,42 @@ class SlabRank(object):
             wj = pl.w_count(j)
             _copy3d(blk, 0, self.volB[v], pl.cols[j][0] * gl, pl.H, wj, gl, wj * gl, gl, pl.W * gl, gl)
 
+    # ---- the same re-partitions over peer memory: no staging, no unpacking --------------------------------
+    def push_rows(self, bases):
+        """d-slabs -> row slabs: my disparities of rank j's rows go straight into rank j's row slab."""
+        pl = self.plan
+        gme = pl.g_count(self.rank)
+        for v in range(2):
+            for j, (lo, hi) in enumerate(pl.rows):
+                dst = bases[j] + 4 * (2 + v) * self.region + 16 * pl.granules[self.rank][0]
+                _ffi.call("mccnn_copy3d", ctypes.c_void_p(self.volB[v].data_ptr() + 4 * lo * pl.W * self.Dlp),
+                          ctypes.c_void_p(dst), 1, (hi - lo) * pl.W, gme, 0, gme, 0, pl.G, _ffi.stream_ptr())
+
+    def _tables(self, bases, first_region, bounds):
+        n = self.plan.world
+        b = (ctypes.c_int * (n + 1))(*bounds)
+        left = (ctypes.c_void_p * n)(*[bases[j] + 4 * first_region * self.region for j in range(n)])
+        right = (ctypes.c_void_p * n)(*[bases[j] + 4 * (first_region + 1) * self.region for j in range(n)])
+        return n, b, left, right
+
+    def sgm_rows_to(self, bases):
+        """(0,1) in place, then (0,-1) storing every pixel into the column slab of the rank that owns its column."""
+        p, call, sp, hp, pl = _ffi.ptr, _ffi.call, _ffi.stream_ptr, self.hp, self.plan
+        off = 4 * self.h0 * pl.W
+        n, b, left, right = self._tables(bases, 4, [lo for lo, _ in pl.cols] + [pl.W])
+        call("mccnn_sgm_passes_slab_to", p(self.rowv[0]), p(self.rowv[1]), ctypes.c_void_p(self.img[0].data_ptr() + off),
+             ctypes.c_void_p(self.img[1].data_ptr() + off), p(self.sgm_flags), pl.D, self.h1 - self.h0, pl.W, 0, pl.W, 0,
+             float(hp["sgm_P1"]), float(hp["sgm_P2"]), float(hp["sgm_Q1"]), float(hp["sgm_Q2"]), float(hp["sgm_D"]),
+             float(hp["sgm_V"]), n, b, left, right, self.h0, sp())
+
+    def sgm_cols_to(self, bases):
+        """(-1,0) in place, then (1,0) storing every granule into the disparity slab of the rank that owns it."""
+        p, call, sp, hp, pl = _ffi.ptr, _ffi.call, _ffi.stream_ptr, self.hp, self.plan
+        n, b, left, right = self._tables(bases, 0, [lo for lo, _ in pl.granules] + [pl.G])
+        call("mccnn_sgm_passes_slab_to", p(self.colv[0]), p(self.colv[1]), p(self.img[0]), p(self.img[1]), p(self.sgm_flags),
+             pl.D, pl.H, pl.W, self.w0, self.w1 - self.w0, 1, float(hp["sgm_P1"]), float(hp["sgm_P2"]),
+             float(hp["sgm_Q1"]), float(hp["sgm_Q2"]), float(hp["sgm_D"]), float(hp["sgm_V"]), n, b, left, right, 0, sp())
+
     def cbca2(self, v):
         """CBCA x iters2 of volume v (match.py:154-155)."""
         self._cbca(v, self.volB, self.volA, int(self.hp["cbca_num_iterations2"]))
@@ -427,26 +506,84 @@ def run_slabs(ranks, comm, marks=None):
     return out
 
 
+def run_slabs_p2p(ranks, comm, marks=None):
+    """run_slabs with the three re-partitions done over peer memory (the ranks' volumes live in arenas obtained
+    from comm.make_arenas): the d-slab -> row-slab step is one strided copy per peer into the peer's row slab, and
+    the two SGM hand-overs are fused into the passes themselves -- the last horizontal pass stores each pixel into
+    the column slab of the rank that owns its column, the last vertical pass each granule into the disparity slab of
+    the rank that owns it -- so the transfers ride under the recurrence and nothing is packed, staged or unpacked.
+    A device-side barrier separates the phases."""
+    def mark(name):
+        if marks is not None:
+            ev = ranks[0].torch.cuda.Event(enable_timing=True)
+            ev.record()
+            marks.append((name, ev))
+
+    mark("start")
+    for r in ranks:
+        r.features_band()
+    if ranks[0].plan.world > 1:
+        hf = [comm.exchange_begin([r.send_features(i) for r in ranks], [r.recv_features(i) for r in ranks]) for i in range(2)]
+        for h in hf:
+            comm.exchange_end(h)
+    mark("features")
+    for r in ranks:
+        r.front()
+    mark("front")
+    bases = [comm.peer_bases(i) for i in range(len(ranks))]
+    for r, b in zip(ranks, bases):
+        r.push_rows(b)
+    comm.barrier()
+    for r, b in zip(ranks, bases):
+        r.sgm_rows_to(b)
+    comm.barrier()
+    for r, b in zip(ranks, bases):
+        r.sgm_cols_to(b)
+    comm.barrier()
+    mark("sgm_and_exchanges")
+    for r in ranks:
+        for v in range(2):
+            r.cbca2(v)
+    mark("cbca2")
+    gathered = comm.all_gather([r.wta() for r in ranks])
+    comm.all_reduce_sum([r.combine(g) for r, g in zip(ranks, gathered)])
+    out = [r.finish() for r in ranks]
+    comm.barrier()                                   # (nobody starts the next pair's pushes before every rank is done)
+    mark("wta_refine")
+    return out
+
+
 class SlabMatcher(object):
     """This process's rank of a disparity-slab partitioned pair under torch.distributed."""
 
-    def __init__(self, H, W, ndisp, checkpoint=None, **hp):
+    def __init__(self, H, W, ndisp, checkpoint=None, transport="p2p", **hp):
+        """transport "p2p": volumes in symmetric memory, re-partitions fused into the kernels over NVLink peer
+        stores; "nccl": staged exchanges with grouped ncclSend/ncclRecv."""
+        assert transport in ("p2p", "nccl")
+        self.transport = transport
         self.comm = DistComm()
         self.plan = SlabPlan(H, W, ndisp, self.comm.world)
-        self.rank = SlabRank(self.plan, self.comm.rank, checkpoint=checkpoint, **hp)
+        arena = None
+        if transport == "p2p":
+            arena = self.comm.make_arenas(6 * self.plan.region_floats())[0]
+        self.rank = SlabRank(self.plan, self.comm.rank, checkpoint=checkpoint, arena=arena, **hp)
         self.H, self.W, self.D = self.plan.H, self.plan.W, self.plan.D
         self.hp = self.rank.hp
 
     def set_images(self, left_image, right_image):
         self.rank.set_images(left_image, right_image)
 
+    def _run(self, marks=None):
+        fn = run_slabs_p2p if self.transport == "p2p" else run_slabs
+        return fn([self.rank], self.comm, marks)[0]
+
     def run(self):
-        return run_slabs([self.rank], self.comm)[0]
+        return self._run()
 
     def run_timed(self):
         """run() with a CUDA event after every phase: {phase: milliseconds} on this rank."""
         marks = []
-        run_slabs([self.rank], self.comm, marks)
+        self._run(marks)
         self.rank.torch.cuda.synchronize()
         return {name: marks[i - 1][1].elapsed_time(ev) for i, (name, ev) in enumerate(marks) if i > 0}
 

@@ -15,20 +15,25 @@ ok = True
 for (H, W, D) in ((96, 200, 64), (130, 333, 100)):
     li, ri = synth_pair(H, W, 9, seed=1)
     one = pkg.StereoMatcher(H, W, D); one.set_images(li, ri); want = one.run().clone()
-    sm = pkg.SlabMatcher(H, W, D); sm.set_images(li, ri); got = sm.run()
-    torch.cuda.synchronize()
-    same = bool(torch.equal(got, want))
-    ok = ok and same
-    print("rank %d: %dx%dx%d over %d ranks: slab map == single-GPU map: %s" % (rank, H, W, D, world, same), flush=True)
-    del one, sm
+    for transport in ("nccl", "p2p"):
+        sm = pkg.SlabMatcher(H, W, D, transport=transport); sm.set_images(li, ri)
+        sm.run(); got = sm.run()
+        torch.cuda.synchronize()
+        same = bool(torch.equal(got, want))
+        ok = ok and same
+        print("rank %d: %dx%dx%d over %d ranks (%s): slab map == single-GPU map: %s" % (rank, H, W, D, world, transport, same), flush=True)
+        del sm
+    del one
 H, W, D = 1024, 1536, 256
 li, ri = synth_pair(H, W, 37, seed=0)
-sm = pkg.SlabMatcher(H, W, D); sm.set_images(li, ri)
-for _ in range(2):
-    sm.run()
-t = sm.run_timed()
-if rank == 0:
-    print("phases (ms) at %dx%dx%d over %d ranks:" % (H, W, D, world), {k: round(v, 3) for k, v in t.items()}, "total %.2f" % sum(t.values()), flush=True)
+for transport in ("nccl", "p2p"):
+    sm = pkg.SlabMatcher(H, W, D, transport=transport); sm.set_images(li, ri)
+    for _ in range(2):
+        sm.run()
+    t = sm.run_timed()
+    if rank == 0:
+        print("phases (ms) at %dx%dx%d over %d ranks, %s:" % (H, W, D, world, transport), {k: round(v, 3) for k, v in t.items()}, "total %.2f" % sum(t.values()), flush=True)
+    del sm
 flag = torch.tensor([1 if ok else 0], device="cuda")
 dist.all_reduce(flag, op=dist.ReduceOp.MIN)
 dist.barrier()

@@ -78,6 +78,33 @@ def test_slab_partition_equals_single_gpu_pipeline(pkg, H, W, D, world):
     assert torch.equal(ranks[0].disp[0], one.disp[0]) and torch.equal(ranks[-1].disp[1], one.disp[1])
 
 
+@pytest.mark.parametrize("H,W,D,world", [(40, 96, 48, 2), (33, 75, 37, 3), (48, 130, 100, 4), (21, 64, 31, 8)])
+def test_slab_partition_over_peer_memory_equals_single_gpu_pipeline(pkg, H, W, D, world):
+    """The same partition with the re-partitions fused into the kernels (strided peer copies, SGM passes that store
+    into the next owner's slab): still the single-GPU map and volumes, bit for bit."""
+    import torch
+    li, ri = synth_images(H + W + D, H, W, 40, 3)
+    one = pkg.StereoMatcher(H, W, D)
+    one.set_images(li, ri)
+    want = one.run().clone()
+    plan = pkg.SlabPlan(H, W, D, world)
+    comm = pkg.LocalComm(world)
+    arenas = comm.make_arenas(6 * plan.region_floats())
+    ranks = [pkg.SlabRank(plan, r, arena=arenas[r]) for r in range(world)]
+    for rk in ranks:
+        rk.set_images(li, ri)
+    for _ in range(2):                                        # twice: the arenas are reused from pair to pair
+        maps = pkg.run_slabs_p2p(ranks, comm)
+    torch.cuda.synchronize()
+    full = one.final_volume
+    for r, rk in enumerate(ranks):
+        b, c = plan.d_base(r), plan.d_count(r)
+        for v in range(2):
+            assert torch.equal(rk.volA[v][:, :, :c], full[v][:, :, b:b + c]), (r, v)
+    for m in maps:
+        assert torch.equal(m, want)
+
+
 def test_slab_sgm_passes_match_whole_image_passes(pkg, pf):
     """Row slabs under the horizontal passes and column slabs under the vertical passes reproduce the whole-image
     passes (pf:195-208) exactly, including the other image's penalty look-up across the slab edge."""
