@@ -149,6 +149,14 @@ int mccnn_bilateral(const float *img, const float *in, float *out, const float *
 int mccnn_cost_volume_slab(const float *fl, const float *fr, float *L, float *R,
                            int H, int W, int C, int D, int d_base, int d_count, void *stream);
 
+/* a5 on a disparity slab whose result is re-partitioned into row slabs right after: `iters` rounds of the default
+ * (two streaming passes) mode, the last column pass storing row h into dst[r] for row_bounds[r] <= h <
+ * row_bounds[r+1] -- a row slab [rows_r][W][4 * g_total] of the owner (peer memory), at granule offset g_offset.
+ * `out` holds the intermediate rounds.  row_bounds (nparts + 1) and dst (nparts device pointers) are HOST arrays. */
+int mccnn_cbca_to(const float *in, float *out, float *scratch, const uint8_t *arms, const int32_t *count,
+                  int D, int H, int W, int iters, int nparts, const int *row_bounds, float *const *dst,
+                  int g_offset, int g_total, void *stream);
+
 /* a6/a7: two of the four chained passes (pf:194-208).  which = 0: (0,1) then (0,-1) on a ROW slab -- volumes
  * [H][W][Dp] and images hold the slab's H rows, w_base = 0, w_count = W.  which = 1: (-1,0) then (1,0) on a COLUMN
  * slab -- volumes [H][w_count][Dp] hold image columns [w_base, w_base + w_count), images are whole [H][W].

@@ -219,6 +219,19 @@ static int stream_round(const float *src, float *scratch, float *out, const uint
     return MCCNN_OK;
 }
 
+// The last round of a call whose result is re-partitioned: the column pass stores into the row slabs of the owners.
+static int stream_round_to(const float *src, float *scratch, const CsScatter &sc, const uint8_t *arms, const int32_t *count,
+                           int G, int H, int W, cudaStream_t s) {
+    dim3 grid(cdiv(G, CS_GC), cdiv(W, CS_PW), cdiv(H, CS_PH));
+    k_cbca_pass<false, CS_ITEMS, 1><<<grid, CS_THREADS, 0, s>>>(reinterpret_cast<const float4 *>(src), reinterpret_cast<float4 *>(scratch),
+                                                                reinterpret_cast<const uchar4 *>(arms), count, G, H, W);
+    MCCNN_LAUNCHED("cbca_rows");
+    k_cbca_pass<true, CS_ITEMS, 1, true><<<grid, CS_THREADS, 0, s>>>(reinterpret_cast<const float4 *>(scratch), nullptr,
+                                                                     reinterpret_cast<const uchar4 *>(arms), count, G, H, W, sc);
+    MCCNN_LAUNCHED("cbca_cols_scatter");
+    return MCCNN_OK;
+}
+
 }  // namespace mccnn
 
 using namespace mccnn;
@@ -256,6 +269,33 @@ size_t mccnn_cbca_workspace_bytes(int H, int W) {
     const size_t tiled = (size_t)cdiv(W, CT_TW) * cdiv(H, CT_TH) * sizeof(CbcaTileMeta) + CBCA_MAX_ROUNDS * sizeof(unsigned);
     const size_t fused = (size_t)CBCA_MAX_ROUNDS * (1 + 2 * (size_t)cdiv(H, CS_PH)) * sizeof(unsigned);
     return tiled > fused ? tiled : fused;
+}
+
+int mccnn_cbca_to(const float *in, float *out, float *scratch, const uint8_t *arms, const int32_t *count, int D, int H,
+                  int W, int iters, int nparts, const int *row_bounds, float *const *dst, int g_offset, int g_total,
+                  void *stream) {
+    MCCNN_REQUIRE(in && out && scratch && arms && count && D >= 1 && H >= 1 && W >= 1 && iters >= 1, "cbca_to: bad arguments");
+    MCCNN_REQUIRE(in != out && scratch != in && scratch != out, "cbca_to: in, out and scratch must differ");
+    MCCNN_REQUIRE(nparts >= 1 && nparts <= CS_MAX_PARTS && row_bounds && dst, "cbca_to: 1 to %d parts", CS_MAX_PARTS);
+    MCCNN_REQUIRE(row_bounds[0] == 0 && row_bounds[nparts] == H, "cbca_to: row bounds must tile [0, %d)", H);
+    const int G = dpitch(D) / 4;
+    MCCNN_REQUIRE(g_offset >= 0 && g_offset + G <= g_total, "cbca_to: granules [%d, %d) outside the destination pitch %d",
+                  g_offset, g_offset + G, g_total);
+    CsScatter sc;
+    sc.nparts = nparts; sc.g_off = g_offset; sc.g_total = g_total;
+    for (int r = 0; r <= nparts; r++) sc.lo[r] = row_bounds[r];
+    for (int r = 0; r < nparts; r++) {
+        MCCNN_REQUIRE(row_bounds[r] < row_bounds[r + 1] && dst[r], "cbca_to: empty part or null destination %d", r);
+        sc.base[r] = reinterpret_cast<float4 *>(dst[r]);
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    const float *src = in;
+    for (int it = 0; it + 1 < iters; it++) {
+        int rc = stream_round(src, scratch, out, arms, count, G, H, W, s);
+        if (rc) return rc;
+        src = out;
+    }
+    return stream_round_to(src, scratch, sc, arms, count, G, H, W, s);
 }
 
 int mccnn_cbca(const float *in, float *out, float *scratch, const uint8_t *arms, const int32_t *count, int D, int H,

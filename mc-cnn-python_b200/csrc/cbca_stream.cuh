@@ -44,10 +44,20 @@ __device__ __forceinline__ float cs_div1(float a, float n, float y) {
 // on either side of every item travel global -> shared with cp.async: bytes in flight that cost no registers (these
 // kernels are bound by memory-level parallelism, and most arms are 0 or 1 long, so the common walk needs nothing
 // else).  A thread reads back only its own slots: no barrier.
-template <bool COLS, int ITEMS, int NB>
+// Where the column pass of a round stores when the volume is re-partitioned right after it (one big pair over
+// several GPUs, slab.py): row h of this disparity slab goes to the rank that owns row h, into its row slab
+// [rows_r][W][g_total] at granule offset g_off -- peer memory over NVLink, no packing or staging afterwards.
+constexpr int CS_MAX_PARTS = 8;
+struct CsScatter {
+    int nparts, g_off, g_total;
+    int lo[CS_MAX_PARTS + 1];                 // row bounds of the parts
+    float4 *base[CS_MAX_PARTS];
+};
+
+template <bool COLS, int ITEMS, int NB, bool SC = false>
 __global__ void __launch_bounds__(CS_THREADS, CS_MIN_BLOCKS) k_cbca_pass(const float4 *__restrict__ src, float4 *__restrict__ dst,
                                                           const uchar4 *__restrict__ arms, const int32_t *__restrict__ count,
-                                                          int G, int H, int W) {
+                                                          int G, int H, int W, const CsScatter sc = CsScatter()) {
     __shared__ float4 stage[2 * NB + 1][ITEMS][CS_THREADS];      // [centre, -1, +1, -2, +2, ..]
     constexpr int PH = 2 * ITEMS;
     // grid = (granule groups, patch columns, patch rows): the granule groups of a patch are consecutive CTAs, so a
@@ -105,7 +115,14 @@ __global__ void __launch_bounds__(CS_THREADS, CS_MIN_BLOCKS) k_cbca_pass(const f
                 acc = make_float4(acc.x / n[s], acc.y / n[s], acc.z / n[s], acc.w / n[s]);   // pf:161
             }
         }
-        dst[p[s] * G + g] = acc;
+        if (!SC) {
+            dst[p[s] * G + g] = acc;
+        } else {
+            const int h = (int)(p[s] / W), w = (int)(p[s] - (size_t)h * W);
+            int r = 0;
+            while (r + 1 < sc.nparts && h >= sc.lo[r + 1]) r++;
+            sc.base[r][((size_t)(h - sc.lo[r]) * W + w) * sc.g_total + sc.g_off + g] = acc;
+        }
     }
 }
 

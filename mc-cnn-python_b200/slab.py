@@ -285,8 +285,9 @@ class SlabRank(object):
     def recv_features(self, i):
         return [self.feat[i][lo:hi] for lo, hi in self.plan.rows]
 
-    def front(self):
-        """This slab of the cost volume, cross arms, CBCA x iters1 (match.py:137-143)."""
+    def front(self, bases=None):
+        """This slab of the cost volume, cross arms, CBCA x iters1 (match.py:137-143).  With `bases` (the ranks' arena
+        addresses) the last column pass of the aggregation stores straight into the row slabs of the owners."""
         p, call, sp, hp, pl = _ffi.ptr, _ffi.call, _ffi.stream_ptr, self.hp, self.plan
         H, W, D = pl.H, pl.W, pl.D
         call("mccnn_cost_volume_slab", p(self.feat[0]), p(self.feat[1]), p(self.volA[0]), p(self.volA[1]), H, W, 64, D,
@@ -294,8 +295,19 @@ class SlabRank(object):
         for i in range(2):
             call("mccnn_cross_arms", p(self.img[i]), p(self.arms[i]), p(self.count[i]), H, W,
                  ctypes.c_float(np.float32(hp["cbca_intensity"])), int(hp["cbca_distance"]), sp())
+        it1 = int(hp["cbca_num_iterations1"])
+        if bases is None or it1 < 1 or int(hp["cbca_distance"]) > 255:
+            for v in range(2):
+                self._cbca(v, self.volA, self.volB, it1)
+            if bases is not None:
+                self.push_rows(bases)
+            return
+        n = pl.world
+        bounds = (ctypes.c_int * (n + 1))(*([lo for lo, _ in pl.rows] + [H]))
         for v in range(2):
-            self._cbca(v, self.volA, self.volB, int(hp["cbca_num_iterations1"]))
+            dst = (ctypes.c_void_p * n)(*[bases[j] + 4 * (2 + v) * self.region for j in range(n)])
+            call("mccnn_cbca_to", p(self.volA[v]), p(self.volB[v]), p(self.volS), p(self.arms[v]), p(self.count[v]), self.Dl,
+                 H, W, it1, n, bounds, dst, pl.granules[self.rank][0], pl.G, sp())
 
     def _cbca(self, i, src, dst, iters):
         p, call, sp, hp, pl = _ffi.ptr, _ffi.call, _ffi.stream_ptr, self.hp, self.plan
@@ -508,8 +520,9 @@ def run_slabs(ranks, comm, marks=None):
 
 def run_slabs_p2p(ranks, comm, marks=None):
     """run_slabs with the three re-partitions done over peer memory (the ranks' volumes live in arenas obtained
-    from comm.make_arenas): the d-slab -> row-slab step is one strided copy per peer into the peer's row slab, and
-    the two SGM hand-overs are fused into the passes themselves -- the last horizontal pass stores each pixel into
+    from comm.make_arenas): all three hand-overs are fused into
+    the kernels that produce the cells -- the last column pass of the first aggregation stores each row into the row
+    slab of the rank that owns it, the last horizontal pass stores each pixel into
     the column slab of the rank that owns its column, the last vertical pass each granule into the disparity slab of
     the rank that owns it -- so the transfers ride under the recurrence and nothing is packed, staged or unpacked.
     A device-side barrier separates the phases."""
@@ -527,12 +540,10 @@ def run_slabs_p2p(ranks, comm, marks=None):
         for h in hf:
             comm.exchange_end(h)
     mark("features")
-    for r in ranks:
-        r.front()
-    mark("front")
     bases = [comm.peer_bases(i) for i in range(len(ranks))]
     for r, b in zip(ranks, bases):
-        r.push_rows(b)
+        r.front(b)
+    mark("front")
     comm.barrier()
     for r, b in zip(ranks, bases):
         r.sgm_rows_to(b)
