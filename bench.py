@@ -320,7 +320,7 @@ def run_ours(args):
                 "scaling": "strong" if single_pair else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": {"workload": desc, "H": H, "W": W, "D": D, "pairs_per_step": pairs,
                            "parallelism": ("one pair, %d disparity slabs; row / column slabs around SGM (3 NVLink "
-                                           "re-partitions per volume)" % world) if slab else
+                                           "re-partitions per volume, transport %s)" % (world, m.transport)) if slab else
                                           "image-pair data parallel, dp%d" % world,
                            "weights": "random-init (glorot-uniform, seed 0)",
                            "l2": "no explicit flush: each stage streams >= 1.6 GB (volumes are 805 MB each) >> 126 MB L2"},
