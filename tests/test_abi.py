@@ -104,3 +104,33 @@ def test_checkpoint_reader_on_reference_bundle(pkg, features_golden):
     assert np.array_equal(ws[0], g["conv1_weights"]) and np.array_equal(bs[0], g["conv1_biases"])
     assert np.array_equal(bs[4], g["conv5_biases"])
     np.testing.assert_allclose([float(w.astype(np.float64).sum()) for w in ws], g["weight_sums"], rtol=1e-12)
+
+
+def test_slab_entry_points_validate_before_touching_the_device(pkg):
+    """The multi-GPU entry points (one big pair by disparity slab) reject inconsistent partitions on the host."""
+    lib = pkg._ffi.lib()
+    one = ctypes.c_void_p(16)
+    err = lambda: lib.mccnn_last_error()
+    # a slab must lie inside [0, ndisp)
+    assert lib.mccnn_cost_volume_slab(one, one, one, one, 4, 40, 64, 16, 12, 8, None) == -1 and b"slab" in err()
+    # horizontal passes need whole rows; directions come in pairs selected by `which`
+    assert lib.mccnn_sgm_passes_slab(one, one, one, one, one, 8, 4, 20, 2, 10, 0, 1.0, 2.0, 4.0, 8.0, 0.1, 1.5, None) == -1
+    assert b"whole rows" in err()
+    assert lib.mccnn_sgm_passes_slab(one, one, one, one, one, 8, 4, 20, 0, 20, 2, 1.0, 2.0, 4.0, 8.0, 0.1, 1.5, None) == -1
+    # scatter tables: bounds must tile the columns (which = 0) or the granules (which = 1)
+    bad = (ctypes.c_int * 3)(0, 7, 19)
+    dst = (ctypes.c_void_p * 2)(16, 16)
+    rc = lib.mccnn_sgm_passes_slab_to(one, one, one, one, one, 8, 4, 20, 0, 20, 0, 1.0, 2.0, 4.0, 8.0, 0.1, 1.5, 2, bad, dst, dst,
+                                      0, None)
+    assert rc == -1 and b"tile" in err()
+    rc = lib.mccnn_sgm_passes_slab_to(one, one, one, one, one, 8, 4, 20, 0, 20, 0, 1.0, 2.0, 4.0, 8.0, 0.1, 1.5, 9, bad, dst, dst,
+                                      0, None)
+    assert rc == -1 and b"parts" in err()
+    rows = (ctypes.c_int * 3)(0, 2, 5)
+    rc = lib.mccnn_cbca_to(one, ctypes.c_void_p(32), ctypes.c_void_p(48), one, one, 8, 4, 20, 2, 2, rows, dst, 0, 2, None)
+    assert rc == -1 and b"tile" in err()
+    rows = (ctypes.c_int * 3)(0, 2, 4)
+    rc = lib.mccnn_cbca_to(one, ctypes.c_void_p(32), ctypes.c_void_p(48), one, one, 8, 4, 20, 2, 2, rows, dst, 1, 2, None)
+    assert rc == -1 and b"pitch" in err()
+    assert lib.mccnn_wta_combine(one, one, one, 2, 3, 2, 2, None) == -1                 # slab stride smaller than a map
+    assert lib.mccnn_copy3d(ctypes.c_void_p(8), one, 1, 1, 1, 0, 0, 0, 0, None) == -1 and b"aligned" in err()
