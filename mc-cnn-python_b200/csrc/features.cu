@@ -12,35 +12,38 @@ namespace mccnn {
 
 constexpr int F = 64;              // feature maps (model.py:38)
 
-// Layer 1: 1 -> 64.  One thread per (output pixel, 4 output channels).
+// Layer 1: 1 -> 64.  A thread owns 4 output channels -- their 36 weights and 4 biases stay in registers -- and
+// walks C1_PX pixels of a row, 16 apart (the 16 channel quads of a pixel are 16 consecutive lanes: every store of a
+// warp is 512 contiguous bytes).  grid = (pixel groups of a row, rows).
+constexpr int C1_PX = 8;
 __global__ void __launch_bounds__(256) k_conv1(const float *__restrict__ img, const float *__restrict__ wgt,
                                                const float *__restrict__ bias, float *__restrict__ out, int H, int W,
                                                int pad, int OH, int OW, int relu) {
-    __shared__ float ws[9 * F];
-    __shared__ float bs[F];
-    for (int i = threadIdx.x; i < 9 * F; i += blockDim.x) ws[i] = wgt[i];
-    for (int i = threadIdx.x; i < F; i += blockDim.x) bs[i] = bias[i];
-    __syncthreads();
-    long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    long long px = t >> 4;
-    int oc = (int)(t & 15) * 4;
-    if (px >= (long long)OH * OW) return;
-    int y = (int)(px / OW), x = (int)(px % OW);
-    float4 acc = make_float4(bs[oc], bs[oc + 1], bs[oc + 2], bs[oc + 3]);
-    float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int oc = (threadIdx.x & 15) * 4, slot = threadIdx.x >> 4, y = blockIdx.y;
+    float4 wv[9];
 #pragma unroll
-    for (int ky = 0; ky < 3; ky++)
+    for (int t = 0; t < 9; t++) wv[t] = *reinterpret_cast<const float4 *>(wgt + t * F + oc);
+    const float4 bv = *reinterpret_cast<const float4 *>(bias + oc);
+    float4 *orow = reinterpret_cast<float4 *>(out) + (size_t)y * OW * 16 + (oc >> 2);
+#pragma unroll 2
+    for (int it = 0; it < C1_PX; it++) {
+        const int x = (blockIdx.x * C1_PX + it) * 16 + slot;
+        if (x >= OW) break;
+        float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-        for (int kx = 0; kx < 3; kx++) {
-            int iy = y + ky - pad, ix = x + kx - pad;             // coordinates in the unpadded image
-            float v = (iy >= 0 && iy < H && ix >= 0 && ix < W) ? img[(size_t)iy * W + ix] : 0.0f;
-            const float *wp = ws + (ky * 3 + kx) * F + oc;
-            sum.x = fmaf(v, wp[0], sum.x); sum.y = fmaf(v, wp[1], sum.y);
-            sum.z = fmaf(v, wp[2], sum.z); sum.w = fmaf(v, wp[3], sum.w);
-        }
-    acc.x += sum.x; acc.y += sum.y; acc.z += sum.z; acc.w += sum.w;
-    if (relu) { acc.x = fmaxf(acc.x, 0.f); acc.y = fmaxf(acc.y, 0.f); acc.z = fmaxf(acc.z, 0.f); acc.w = fmaxf(acc.w, 0.f); }
-    reinterpret_cast<float4 *>(out)[px * 16 + (oc >> 2)] = acc;
+        for (int ky = 0; ky < 3; ky++)
+#pragma unroll
+            for (int kx = 0; kx < 3; kx++) {
+                const int iy = y + ky - pad, ix = x + kx - pad;   // coordinates in the unpadded image
+                const float v = (iy >= 0 && iy < H && ix >= 0 && ix < W) ? img[(size_t)iy * W + ix] : 0.0f;
+                const float4 w4 = wv[ky * 3 + kx];
+                sum.x = fmaf(v, w4.x, sum.x); sum.y = fmaf(v, w4.y, sum.y);
+                sum.z = fmaf(v, w4.z, sum.z); sum.w = fmaf(v, w4.w, sum.w);
+            }
+        float4 acc = make_float4(bv.x + sum.x, bv.y + sum.y, bv.z + sum.z, bv.w + sum.w);
+        if (relu) { acc.x = fmaxf(acc.x, 0.f); acc.y = fmaxf(acc.y, 0.f); acc.z = fmaxf(acc.z, 0.f); acc.w = fmaxf(acc.w, 0.f); }
+        orow[(size_t)x * 16] = acc;
+    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -352,9 +355,9 @@ int mccnn_features(const float *img, int H, int W, int pad, int num_layers, cons
     float *wsplit = buf[0] ? buf[1] + (size_t)oh * ow * F : nullptr;
     float *dst = (num_layers == 1) ? out : buf[0];
     {
-        long long threads = (long long)oh * ow * 16;
-        k_conv1<<<cdiv(threads, 256), 256, 0, s>>>(img, weights_host[0], biases_host[0], dst, H, W, pad, oh, ow,
-                                                   num_layers > 1);
+        MCCNN_REQUIRE(oh <= 65535, "features: image too tall (%d rows)", oh);
+        k_conv1<<<dim3(cdiv(ow, 16 * C1_PX), oh), 256, 0, s>>>(img, weights_host[0], biases_host[0], dst, H, W, pad, oh, ow,
+                                                                        num_layers > 1);
         MCCNN_LAUNCHED("conv1");
     }
     if (num_layers == 1) {
