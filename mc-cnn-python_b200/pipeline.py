@@ -88,11 +88,18 @@ class StereoMatcher(object):
         f = ctypes.c_float
         img, feat = self.img, self.feat
 
+        def make_feature(i):
+            def feature():
+                call("mccnn_features", p(img[i]), H, W, self.pad, self.pad, self.weights.w_table,
+                     self.weights.b_table, p(feat[i]), p(self.feat_scratch), sp())
+            return feature
+
+        self._feature_fns = [make_feature(0), make_feature(1)]
+
         def make_features():
             def features():
-                for i in range(2):
-                    call("mccnn_features", p(img[i]), H, W, self.pad, self.pad, self.weights.w_table,
-                         self.weights.b_table, p(feat[i]), p(self.feat_scratch), sp())
+                for fn in self._feature_fns:
+                    fn()
             return features
 
         def make_cost_volume(vol):
@@ -223,13 +230,27 @@ class StereoMatcher(object):
     def run_host(self, left_image, right_image):
         """NumPy images in, NumPy disparity out: H2D from pinned memory, hot path, D2H, one sync."""
         torch = self.torch
+        with_features = "features" in self.stages
+        cur = torch.cuda.current_stream()
+        if not hasattr(self, "_copy_stream"):
+            self._copy_stream = torch.cuda.Stream()
+            self._copy_events = [torch.cuda.Event(), torch.cuda.Event()]
+        self._copy_stream.wait_stream(cur)          # (earlier work on this stream may still read the images)
         for i, im in enumerate((left_image, right_image)):
             a = np.asarray(im, dtype=np.float32)
             if a.ndim == 3:
                 a = a[:, :, 0]
             self.host_in[i].numpy()[...] = a
-            self.img[i].copy_(self.host_in[i], non_blocking=True)
-        d = self.run()
+            with torch.cuda.stream(self._copy_stream):
+                self.img[i].copy_(self.host_in[i], non_blocking=True)
+                self._copy_events[i].record(self._copy_stream)
+            cur.wait_event(self._copy_events[i])
+            if with_features:
+                self._feature_fns[i]()          # the left image's features run while the right image is staged and copied
+        for name, fn in self._steps:
+            if name != "features":
+                fn()
+        d = self.result
         self.host_out.copy_(d, non_blocking=True)
         torch.cuda.current_stream().synchronize()
         return self.host_out.numpy().copy()
