@@ -57,6 +57,9 @@ def build_parser():
     p.add_argument("--sgm_V", type=float, default=1.5)
     p.add_argument("--blur_sigma", type=float, default=6)
     p.add_argument("--blur_threshold", type=float, default=2)
+    # not in the reference: under torchrun, share EVERY pair among all ranks by disparity slab (one big pair over
+    # several GPUs, slab.py) instead of giving each rank its own window of pairs
+    p.add_argument("--slab", action="store_true")
     return p
 
 
@@ -95,7 +98,16 @@ def main(argv=None):
 
     # the reference's window is [start, end] inclusive (match.py:85-90); split it across ranks
     first, last = max(args.start, 0), min(args.end, len(img_paths) - 1)
-    lo, hi = pipeline.shard_window(max(last - first + 1, 0), rank, world)
+    slab_mode = bool(args.slab) and world > 1
+    if slab_mode:
+        import torch.distributed as dist
+        import slab                                                                # this directory's slab.py
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if not dist.is_initialized():
+            dist.init_process_group("nccl", device_id=torch.device("cuda", torch.cuda.current_device()))
+        lo, hi = 0, max(last - first + 1, 0)                                       # every rank works on every pair
+    else:
+        lo, hi = pipeline.shard_window(max(last - first + 1, 0), rank, world)
     hp = dict(patch_size=args.patch_size, cbca_intensity=args.cbca_intensity,
               cbca_distance=_as_int("cbca_distance", args.cbca_distance),
               cbca_num_iterations1=_as_int("cbca_num_iterations1", args.cbca_num_iterations1),
@@ -120,11 +132,16 @@ def main(argv=None):
         assert right_image.shape == (height, width, 1)
         key = (height, width, ndisp)
         if key not in matchers:
-            matchers[key] = pipeline.StereoMatcher(height, width, ndisp, checkpoint=args.resume, **hp)
+            if slab_mode:
+                matchers[key] = slab.SlabMatcher(height, width, ndisp, checkpoint=args.resume, **hp)
+            else:
+                matchers[key] = pipeline.StereoMatcher(height, width, ndisp, checkpoint=args.resume, **hp)
         torch.cuda.synchronize()
         st = time.time()                                                           # match.py:129
         disparity = matchers[key].run_host(left_image, right_image)                # match.py:131-175
         elapsed = time.time() - st                                                 # match.py:179
+        if slab_mode and rank != 0:
+            continue                                                               # rank 0 writes the shared pair
         util.saveDisparity(disparity, os.path.join(img_dir, out_img_file))         # match.py:182-184
         util.writePfm(disparity, os.path.join(res_dir, out_file))
         util.saveTimeFile(elapsed, os.path.join(res_dir, out_time_file))
