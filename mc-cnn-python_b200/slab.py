@@ -582,7 +582,21 @@ class SlabMatcher(object):
         self.transport = transport
         arena = None
         if transport == "p2p":
-            arena = self.comm.make_arenas(6 * self.plan.region_floats())[0]
+            # symmetric memory is a young torch API: every rank tries, and all fall back to the staged NCCL
+            # transport together if any of them cannot map its peers (still GPU to GPU, never through the host)
+            import torch
+            ok, why = 1, ""
+            try:
+                arena = self.comm.make_arenas(6 * self.plan.region_floats())[0]
+            except (ImportError, AttributeError, RuntimeError) as e:
+                ok, why, arena = 0, repr(e), None
+            flag = torch.tensor([ok], dtype=torch.int32, device="cuda")
+            self.comm.dist.all_reduce(flag, op=self.comm.dist.ReduceOp.MIN)
+            if int(flag.item()) == 0:
+                if self.comm.rank == 0:
+                    print("slab: peer-memory transport unavailable (%s); using staged NCCL exchanges" % (why or "on another rank"))
+                arena, transport = None, "nccl"
+                self.transport = transport
         self.rank = SlabRank(self.plan, self.comm.rank, checkpoint=checkpoint, arena=arena, **hp)
         self.H, self.W, self.D = self.plan.H, self.plan.W, self.plan.D
         self.hp = self.rank.hp
