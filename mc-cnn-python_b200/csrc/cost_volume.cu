@@ -72,12 +72,16 @@ __device__ __forceinline__ void cv_store_quarter(float *__restrict__ vol, unsign
 #pragma unroll
             for (int j = 0; j < 32; j++) p[(ptrdiff_t)j * (Dp + DN)] = __uint_as_float(v[j]);
         } else {
+            // columns j whose cell exists: 0 <= dl + DN*j < D and 0 <= pix0 + n0 + j < W is one interval [ja, jb) per
+            // lane; as a bit mask it costs one test per store instead of two index computations and two compares
+            int ja = max(0, -(pix0 + n0)), jb = min(32, W - (pix0 + n0));
+            if (DN > 0) { ja = max(ja, -dl); jb = min(jb, D - dl); }
+            else        { ja = max(ja, dl - D + 1); jb = min(jb, dl + 1); }
+            unsigned mask = 0;
+            if (lane_ok && jb > ja) mask = (jb - ja >= 32 ? 0xffffffffu : ((1u << (jb - ja)) - 1u)) << ja;
 #pragma unroll
-            for (int j = 0; j < 32; j++) {
-                const int d = dl + DN * j, pix = pix0 + n0 + j;
-                if (lane_ok && (unsigned)d < (unsigned)D && (unsigned)pix < (unsigned)W)
-                    p[(ptrdiff_t)j * (Dp + DN)] = __uint_as_float(v[j]);
-            }
+            for (int j = 0; j < 32; j++)
+                if (mask & (1u << j)) p[(ptrdiff_t)j * (Dp + DN)] = __uint_as_float(v[j]);
         }
     }
 }
