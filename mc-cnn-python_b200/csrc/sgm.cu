@@ -154,19 +154,27 @@ __global__ void __launch_bounds__(32, 16) k_sgm_pass(const __grid_constant__ Sgm
             if (d + 3 >= D) v.w = INF;
         }
     };
-    // cells of step t -> ring slot t % CP (one cp.async group per step, empty past the end of the scanline)
-    auto prefetch_cells = [&](int t) {
+    // cells of step t -> ring slot t % CP (one cp.async group per step, empty past the end of the scanline).  The slot
+    // and the cell addresses are carried from step to step (no division, no 64-bit multiply in the recurrence).
+    const long long stepG = pstride * G;                             // granules between consecutive pixels of the scanline
+    const float4 *pre[JP];                                           // this lane's granules of the next step to prefetch
+    float4 *cellp[JP];                                               // ... of the step being computed (in-place store)
+#pragma unroll
+    for (int j = 0; j < JP; j++) {
+        pre[j] = vol4 + (p0 + pstride) * G + g[j];                   // step 1
+        cellp[j] = vol4 + (p0 + pstride) * G + g[j];
+    }
+    auto prefetch_cells = [&](int t, int slot) {                     // must be called for t = 1, 2, 3, .. in order
         if (t < N) {
-            const long long p = p0 + (long long)t * pstride;
-            const int slot = t % CP;
 #pragma unroll
             for (int j = 0; j < JP; j++)
-                if (gv[j]) sgm_cp_async16(&cring[slot][j][lane], &vol4[p * G + g[j]]);
+                if (gv[j]) sgm_cp_async16(&cring[slot][j][lane], pre[j]);
         }
+#pragma unroll
+        for (int j = 0; j < JP; j++) pre[j] += stepG;
         asm volatile("cp.async.commit_group;\n" ::: "memory");
     };
-    auto take_cells = [&](int t, float4 (&dst)[JP]) {
-        const int slot = t % CP;
+    auto take_cells = [&](int slot, float4 (&dst)[JP]) {
 #pragma unroll
         for (int j = 0; j < JP; j++) {
             float4 v = make_float4(INF, INF, INF, INF);
@@ -181,37 +189,40 @@ __global__ void __launch_bounds__(32, 16) k_sgm_pass(const __grid_constant__ Sgm
     // selectors of this lane's granules (bit k <-> d = 4g + k) are extracted only when the step is executed, so
     // that the loads are never waited for at issue.
     struct FlagWords { uint32_t lo[JP], hi[JP], own; };
-    auto flag_pos = [&](int t, int &pos1) {
-        const int wb = prm.wbase + w0 + t * dw + woff;
-        pos1 = prm.PADW * 32 + wb;
-        return h0 + t * dh + hoff;
-    };
-    auto load_flags = [&](int t, FlagWords &fw) {
-        int pos1;
-        const int hb = flag_pos(t, pos1);
-        const uint32_t *orow = job.oth_map + (size_t)hb * WR;
-        fw.own = job.own_map[(size_t)hb * WR + (pos1 >> 5)];
+    // Bit positions and bit-map rows are carried from step to step: the load stream runs PF steps ahead of the
+    // extract stream, both start at step 1 and advance by one step per call.
+    int goff[JP];                                                    // bit offset of this lane's granule: x = wb -/+ d
 #pragma unroll
-        for (int j = 0; j < JP; j++) {
-            fw.lo[j] = 0; fw.hi[j] = 0;
-            if (gv[j]) {
-                const int pos = job.is_left ? pos1 - 4 * g[j] - 3 : pos1 + 4 * g[j];   // x = wb - d (d = 4g+3 .. 4g) | x = wb + d
-                fw.lo[j] = orow[pos >> 5];
-                fw.hi[j] = orow[(pos >> 5) + 1];
+    for (int j = 0; j < JP; j++) goff[j] = job.is_left ? -4 * g[j] - 3 : 4 * g[j];
+    const int pos_step1 = prm.PADW * 32 + prm.wbase + w0 + dw + woff;               // pos1 of step 1
+    const long long row_step = (long long)dh * WR;
+    int ld_pos1 = pos_step1, ex_pos1 = pos_step1;
+    const uint32_t *ld_own = job.own_map + (long long)(h0 + dh + hoff) * WR;        // bit-map rows of step 1
+    const uint32_t *ld_oth = job.oth_map + (long long)(h0 + dh + hoff) * WR;
+    auto load_flags = [&](bool valid, FlagWords &fw) {
+        if (valid) {
+            fw.own = ld_own[ld_pos1 >> 5];
+#pragma unroll
+            for (int j = 0; j < JP; j++) {
+                fw.lo[j] = 0; fw.hi[j] = 0;
+                if (gv[j]) {
+                    const int pos = ld_pos1 + goff[j];
+                    fw.lo[j] = ld_oth[pos >> 5];
+                    fw.hi[j] = ld_oth[(pos >> 5) + 1];
+                }
             }
         }
+        ld_pos1 += dw; ld_own += row_step; ld_oth += row_step;
     };
-    auto extract_flags = [&](int t, const FlagWords &fw, uint32_t (&dst)[JP], uint32_t &own) {
-        int pos1;
-        (void)flag_pos(t, pos1);
-        own = (fw.own >> (pos1 & 31)) & 1u;
+    auto extract_flags = [&](const FlagWords &fw, uint32_t (&dst)[JP], uint32_t &own) {
+        own = (fw.own >> (ex_pos1 & 31)) & 1u;
 #pragma unroll
         for (int j = 0; j < JP; j++) {
-            const int pos = job.is_left ? pos1 - 4 * g[j] - 3 : pos1 + 4 * g[j];
-            uint32_t f = __funnelshift_r(fw.lo[j], fw.hi[j], pos & 31) & 15u;
+            uint32_t f = __funnelshift_r(fw.lo[j], fw.hi[j], (ex_pos1 + goff[j]) & 31) & 15u;
             if (job.is_left) f = __brev(f) >> 28;
             dst[j] = f;
         }
+        ex_pos1 += dw;
     };
 
     // step 0: the first pixel of the scanline is left unchanged (pf:485-501) and seeds the recurrence
@@ -229,7 +240,8 @@ __global__ void __launch_bounds__(32, 16) k_sgm_pass(const __grid_constant__ Sgm
         }
     }
 #pragma unroll 1
-    for (int t = 1; t <= DIST; t++) prefetch_cells(t);
+    for (int t = 1; t <= DIST; t++) prefetch_cells(t, t);           // (DIST < CP: slot = t)
+    int slot_t = 1;                                                  // ring slot of the step being computed
     float m;
     {
         float lm = INF;
@@ -241,7 +253,7 @@ __global__ void __launch_bounds__(32, 16) k_sgm_pass(const __grid_constant__ Sgm
     FlagWords fring[PF];
 #pragma unroll
     for (int u = 0; u < PF; u++)
-        if (1 + u < N) load_flags(1 + u, fring[u]);
+        load_flags(1 + u < N, fring[u]);
 
     for (int t0 = 1; t0 < N; t0 += PF) {
 #pragma unroll
@@ -252,11 +264,12 @@ __global__ void __launch_bounds__(32, 16) k_sgm_pass(const __grid_constant__ Sgm
                 uint32_t fb[JP];
 #pragma unroll
                 uint32_t f1;
-                extract_flags(t, fring[u], fb, f1);
-                if (t + PF < N) load_flags(t + PF, fring[u]);
+                extract_flags(fring[u], fb, f1);
+                load_flags(t + PF < N, fring[u]);
                 asm volatile("cp.async.wait_group %0;\n" ::"n"(DIST - 1) : "memory");     // the cells of step t have landed
-                take_cells(t, cur);
-                prefetch_cells(t + DIST);                                                  // into the slot step t - 1 used
+                take_cells(slot_t, cur);
+                prefetch_cells(t + DIST, slot_t == 0 ? CP - 1 : slot_t - 1);               // into the slot step t - 1 used
+                slot_t = slot_t == CP - 1 ? 0 : slot_t + 1;
 
                 // penalties (pf:535-541): f1 = (D1 >= tauD), per-cell bit = (D2 >= tauD)
                 const float pa1 = f1 ? prm.P1q1 : prm.P1, pb1 = f1 ? prm.P1q2 : prm.P1q1;
@@ -268,7 +281,7 @@ __global__ void __launch_bounds__(32, 16) k_sgm_pass(const __grid_constant__ Sgm
                     rx_[j] = __shfl_sync(0xffffffffu, prev[j].x, src_up);
                 }
                 float lm = INF;
-                const long long p = p0 + (long long)t * pstride;
+                const long long p = SC ? p0 + (long long)t * pstride : 0;
 #pragma unroll
                 for (int j = 0; j < JP; j++) {
                     const float lnb = first_lane ? (j > 0 ? rw_[j > 0 ? j - 1 : 0] : INF) : rw_[j];
@@ -280,7 +293,11 @@ __global__ void __launch_bounds__(32, 16) k_sgm_pass(const __grid_constant__ Sgm
                     o.y = (cur[j].y + fminf(q.y, fminf(fminf(q.x, q.z) + ((b & 2u) ? pb1 : pa1), (b & 2u) ? cB : cA))) - m;
                     o.z = (cur[j].z + fminf(q.z, fminf(fminf(q.y, q.w) + ((b & 4u) ? pb1 : pa1), (b & 4u) ? cB : cA))) - m;
                     o.w = (cur[j].w + fminf(q.w, fminf(fminf(q.z, rnb) + ((b & 8u) ? pb1 : pa1), (b & 8u) ? cB : cA))) - m;
-                    if (gv[j]) store_cell(p, t, j, o);
+                    if (gv[j]) {
+                        if (SC) store_cell(p, t, j, o);
+                        else *cellp[j] = o;
+                    }
+                    cellp[j] += stepG;
                     prev[j] = o;
                     lm = fminf(fminf(lm, fminf(o.x, o.y)), fminf(o.z, o.w));
                 }
