@@ -120,3 +120,28 @@ def test_slab_plan_tiles_everything():
             assert [p.owner_of_disparity(d) for d in (0, D - 1)] == [0, world - 1]
     with pytest.raises(AssertionError):
         pkg.SlabPlan(100, 100, 8, 4)                      # two granules cannot feed four ranks
+
+
+@pytest.mark.parametrize("world,H,W,D", [(2, 9, 14, 22), (3, 7, 11, 31), (4, 8, 9, 40)])
+def test_local_comm_emulation_moves_the_same_blocks(world, H, W, D):
+    """LocalComm (all ranks in one process: what the GPU tests drive the partition with) has the semantics of
+    DistComm: exchange delivers sends[i][j] to recvs[j][i], all_gather stacks in rank order, all_reduce sums."""
+    sys.path.insert(0, ROOT)
+    import importlib
+    pkg = importlib.import_module("mc-cnn-python_b200")
+    plan = pkg.SlabPlan(H, W, D, world)
+    comm = pkg.LocalComm(world)
+    Dp = 4 * plan.G
+    full = torch.zeros(H, W, Dp)
+    full[:, :, :D] = _volume(H, W, D)
+    slabs = [full[:, :, 4 * lo:4 * hi].contiguous() for lo, hi in plan.granules]
+    sends = [[slabs[i][lo:hi].contiguous() for lo, hi in plan.rows] for i in range(world)]
+    recvs = [[torch.empty(plan.h_count(j), W, 4 * plan.g_count(i)) for i in range(world)] for j in range(world)]
+    comm.exchange(sends, recvs)
+    for j, (lo, hi) in enumerate(plan.rows):
+        assert torch.equal(torch.cat(recvs[j], dim=2), full[lo:hi])
+    parts = [torch.full((2, 3), float(r)) for r in range(world)]
+    for g in comm.all_gather(parts):
+        assert g.shape == (world, 2, 3) and all(float(g[r, 0, 0]) == r for r in range(world))
+    comm.all_reduce_sum(parts)
+    assert all(torch.equal(p, torch.full((2, 3), float(sum(range(world))))) for p in parts)
