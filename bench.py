@@ -315,6 +315,10 @@ def run_ours(args):
                     "traffic": (traffic.get(dom) or {}).get("bytes_per_launch") if (H, W, D) == (1024, 1024, 192) else None,
                     "traffic_source": (traffic.get(dom) or {}).get("source"), "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": nbytes / nl, "avg_launch_ms": acc[dom] / nl}
+        if roofline["traffic"]:
+            # what the kernel(s) of one launch actually move (ncu) against the same peak: the default CBCA round is
+            # two passes, i.e. twice the algorithmic bytes, and runs close to copy speed on those
+            roofline["traffic_frac"] = roofline["traffic"] / (roofline["avg_launch_ms"] * 1e-3) / 1e9 / peak
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
                 "scaling": "strong" if single_pair else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
