@@ -16,7 +16,7 @@ namespace mccnn {
 
 constexpr int CS_PH = 8, CS_PW = 4, CS_GC = 16, CS_THREADS = 128;   // patch 8x4 pixels x 16 granules per CTA
 constexpr int CS_MIN_BLOCKS = 8;   // <= 64 registers: 8 CTAs per SM.  Measured at C3 (ms per round): 6 -> 0.673, 7 -> 0.628,
-                                   // 8 -> 0.608, 9 -> 0.647, 10 -> 0.740; other shapes (items per thread, staged
+                                   // 8 -> 0.608, 9 -> 0.647, 10 -> 0.740 (rows / columns tuned separately: 8 / 8 is still best); other shapes (items per thread, staged
                                    // neighbours): (4,1) 0.608, (3,1) 0.621, (2,1) 0.704, (4,2) 0.825, (2,2) 0.735; cp.async.ca 0.737
 
 __device__ __forceinline__ void cs_add(float4 &acc, const float4 v) {
