@@ -78,6 +78,21 @@ def synth_pair(H, W, shift, seed=0):
     return li[..., None], ri[..., None]
 
 
+def flat_pair(H, W, shift, seed=0, block=48):
+    """Worst case for cross-based aggregation: a piece-wise constant image of `block`-pixel squares of
+    random 8-bit levels, so that almost every arm runs to the distance limit (13 pixels at match.py's
+    distance_threshold 14, regions up to 27 x 27 = 729, pf:585-599); normalised as match.py:118-123,
+    right(x) = left(x + shift)."""
+    rng = np.random.default_rng(seed)
+    Wb = W + shift
+    lv = rng.integers(0, 256, ((H + block - 1) // block, (Wb + block - 1) // block)).astype(np.float32)
+    q = np.kron(lv, np.ones((block, block), np.float32))[:H, :Wb]
+    left, right = q[:, :W], q[:, shift:shift + W]
+    li = ((left - np.mean(left, axis=(0, 1))) / np.std(left, axis=(0, 1))).astype(np.float32)
+    ri = ((right - np.mean(right, axis=(0, 1))) / np.std(right, axis=(0, 1))).astype(np.float32)
+    return li[..., None], ri[..., None]
+
+
 def unit_features(H, W, seed=0):
     rng = np.random.default_rng(seed)
     f = rng.standard_normal((2, H, W, 64)).astype(np.float32)

@@ -79,26 +79,17 @@ int mccnn_cross_region_list(const uint8_t *arms, int32_t *region, int H, int W,
 /* ---- a5  pf:117 cost_volume_aggregation, one volume ----
  * `iters` rounds of region mean; in is left untouched, out receives the result, scratch is one
  * more HWD volume.
- * mode MCCNN_CBCA_SEPARABLE: row sums re-used down each column (<= 54 additions per cell); equals the
- *      reference up to float32 re-association of the sum (~1e-7 relative).  Two streaming passes per
- *      round (rows into `scratch`, columns into `out`): `scratch` is needed for any iters >= 1.
- * mode MCCNN_CBCA_SEPARABLE_TILED: the same sums in one fused kernel per round (TMA-staged shared-memory
- *      tiles).  Needs distance_threshold <= 14 (match.py:34 default) and a workspace of
- *      mccnn_cbca_workspace_bytes(H, W) bytes (per-tile halo table and schedule, rebuilt per call).
- * mode MCCNN_CBCA_SEPARABLE_MARCH: the same sums in one row-marching kernel per round (TMA-staged rows, row
- *      sums kept in a thread-private shared-memory ring): every cell read once and written once.  Shapes it
- *      is not built for (distance_threshold > 14, D < 29) take the two streaming passes instead.
- * mode MCCNN_CBCA_SEPARABLE_L2: the two streaming passes as one persistent kernel per round, pipelined over
- *      bands of 8 rows so that the row sums stay in a 64-row ring in L2 (the first rows of `scratch`) instead of
- *      making a round trip through HBM.  Bit-identical to MCCNN_CBCA_SEPARABLE; needs the workspace.
+ * mode MCCNN_CBCA_SEPARABLE (default): row sums re-used down each column (<= 54 additions per cell at
+ *      distance_threshold 14); equals the reference up to float32 re-association of the sum (~1e-7 relative).
+ *      Two streaming passes per round (rows into `scratch`, columns into `out`): `scratch` is needed for any
+ *      iters >= 1.
  * mode MCCNN_CBCA_EXACT: one float32 running sum over the whole region in the reference's enumeration
- *      order (pf:149-163), bit-identical to the reference (<= 729 additions per cell). */
-enum mccnn_cbca_mode { MCCNN_CBCA_SEPARABLE = 0, MCCNN_CBCA_EXACT = 1, MCCNN_CBCA_SEPARABLE_TILED = 2,
-                       MCCNN_CBCA_SEPARABLE_MARCH = 3, MCCNN_CBCA_SEPARABLE_L2 = 4 };
-size_t mccnn_cbca_workspace_bytes(int H, int W);
+ *      order (pf:149-163), bit-identical to the reference (<= 729 additions per cell); `scratch` for iters >= 2.
+ * distance_threshold (1..255) is the value the arms were built with. */
+enum mccnn_cbca_mode { MCCNN_CBCA_SEPARABLE = 0, MCCNN_CBCA_EXACT = 1 };
 int mccnn_cbca(const float *in, float *out, float *scratch, const uint8_t *arms,
                const int32_t *count, int D, int H, int W, int iters, int distance_threshold, int mode,
-               void *workspace, void *stream);
+               void *stream);
 
 /* ---- a6  pf:476 semi_global_matching, one in-place pass over one volume ----
  * (rh, rw) in {(0,1),(0,-1),(-1,0),(1,0)}.  P1/P2/Q1/Q2/tauD arrive as doubles and are rounded to
@@ -150,12 +141,12 @@ int mccnn_cost_volume_slab(const float *fl, const float *fr, float *L, float *R,
                            int H, int W, int C, int D, int d_base, int d_count, void *stream);
 
 /* a5 on a disparity slab whose result is re-partitioned into row slabs right after: `iters` rounds of the default
- * (two streaming passes) mode, the last column pass storing row h into dst[r] for row_bounds[r] <= h <
+ * mode, the closing column pass storing row h into dst[r] for row_bounds[r] <= h <
  * row_bounds[r+1] -- a row slab [rows_r][W][4 * g_total] of the owner (peer memory), at granule offset g_offset.
  * `out` holds the intermediate rounds.  row_bounds (nparts + 1) and dst (nparts device pointers) are HOST arrays. */
 int mccnn_cbca_to(const float *in, float *out, float *scratch, const uint8_t *arms, const int32_t *count,
-                  int D, int H, int W, int iters, int nparts, const int *row_bounds, float *const *dst,
-                  int g_offset, int g_total, void *stream);
+                  int D, int H, int W, int iters, int nparts, const int *row_bounds,
+                  float *const *dst, int g_offset, int g_total, void *stream);
 
 /* a6/a7: two of the four chained passes (pf:194-208).  which = 0: (0,1) then (0,-1) on a ROW slab -- volumes
  * [H][W][Dp] and images hold the slab's H rows, w_base = 0, w_count = W.  which = 1: (-1,0) then (1,0) on a COLUMN

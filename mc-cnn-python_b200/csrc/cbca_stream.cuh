@@ -5,8 +5,9 @@
 // pure gathers with no barriers: the lanes of a warp are consecutive disparity granules of one pixel (two
 // pixels per warp), so every load and store is a contiguous run and an arm walk is warp uniform; neighbouring
 // pixels are served by L2 (a CTA covers an 8x4 pixel patch per 64 disparities).  HBM traffic is 16 B per cell
-// per round -- twice the fused minimum -- but the passes run closer to copy speed than any of the fused
-// kernels tried (cbca_tile.cuh, cbca_march.cuh, cbca_fused.cuh: DESIGN.md 5.3).
+// per round -- twice the fused minimum -- but the passes run closer to copy speed than any of the seven fused
+// kernels tried in rounds 1 and 2 (profiles/r2_cbca_chained_experiment.md): the round is bound by
+// bytes in flight and instruction issue, and every way of keeping a round's result on chip pays in one of the two.
 // Summation order inside a row and along the spine is the reference's; only the association
 // (row sums first) differs: ~1e-7 relative.
 #pragma once

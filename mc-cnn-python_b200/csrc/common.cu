@@ -86,7 +86,7 @@ using namespace mccnn;
 extern "C" {
 
 const char *mccnn_last_error(void) { return g_err; }
-int mccnn_abi_version(void) { return 1; }
+int mccnn_abi_version(void) { return 2; }
 int mccnn_dpitch(int D) { return dpitch(D); }
 unsigned long long mccnn_launch_count(void) { return g_launches.load(); }
 

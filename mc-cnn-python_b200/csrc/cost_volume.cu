@@ -297,17 +297,11 @@ static int cost_volume_slab(const float *fl, const float *fr, float *L, float *R
     if (rc) return rc;
     rc = tc_encode_map_3d(maps.fr, fr, CV_C, W, H, 32, CV_BM, true, "cost_volume");
     if (rc) return rc;
-    static int num_sms = 0;
-    static bool smem_set = false;
-    if (num_sms == 0) {
-        int dev = 0;
-        MCCNN_CUDA(cudaGetDevice(&dev));
-        MCCNN_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
-    }
-    if (!smem_set) {
-        MCCNN_CUDA(cudaFuncSetAttribute(k_cost_volume_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CvSmem)));
-        smem_set = true;
-    }
+    // per device, asked on every call (no process-wide caches: one process may drive several GPUs)
+    int dev = 0, num_sms = 0;
+    MCCNN_CUDA(cudaGetDevice(&dev));
+    MCCNN_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+    MCCNN_CUDA(cudaFuncSetAttribute(k_cost_volume_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CvSmem)));
     const int nwt = cdiv(W, CV_BM), nchunks = cdiv(CV_BM - 1 + D, CV_BN);
     const long long ntiles = (long long)nwt * H;
     MCCNN_REQUIRE(ntiles < (1ll << 31), "cost_volume: image too large");

@@ -366,18 +366,13 @@ int mccnn_features(const float *img, int H, int W, int pad, int num_layers, cons
         MCCNN_LAUNCHED("l2norm64");
         return MCCNN_OK;
     }
-    static int num_sms = 0;
-    static bool smem_set = false;
-    if (num_sms == 0) {
-        int dev = 0;
-        MCCNN_CUDA(cudaGetDevice(&dev));
-        MCCNN_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
-    }
-    if (!smem_set) {
-        MCCNN_CUDA(cudaFuncSetAttribute(k_conv64_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CtcSmem)));
-        MCCNN_CUDA(cudaFuncSetAttribute(k_conv64_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CtcSmem)));
-        smem_set = true;
-    }
+    // per device, asked on every call: the opt-in to > 48 KB of dynamic shared memory belongs to the current device's
+    // context and the persistent grid to its SM count (no process-wide caches: one process may drive several GPUs)
+    int dev = 0, num_sms = 0;
+    MCCNN_CUDA(cudaGetDevice(&dev));
+    MCCNN_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+    MCCNN_CUDA(cudaFuncSetAttribute(k_conv64_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CtcSmem)));
+    MCCNN_CUDA(cudaFuncSetAttribute(k_conv64_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CtcSmem)));
     const float *src = dst;
     int ih = oh, iw = ow;
     for (int l = 1; l < num_layers; l++) {

@@ -61,7 +61,6 @@ class StereoMatcher(object):
         self.volS = e(H, W, Dp) if need_b else None
         self.arms = [e(H, W, 4, dtype=torch.uint8), e(H, W, 4, dtype=torch.uint8)]
         self.count = [e(H, W, dtype=torch.int32), e(H, W, dtype=torch.int32)]
-        self.cbca_ws = _pf.cbca_workspace(H, W)
         ns = int(_ffi.lib().mccnn_sgm_scratch_bytes(H, W, D))
         self.sgm_flags = e((ns + 3) // 4, dtype=torch.int32)
         self.disp = [e(H, W), e(H, W)]
@@ -118,7 +117,7 @@ class StereoMatcher(object):
             def cbca():
                 for i in range(2):
                     call("mccnn_cbca", p(src[i]), p(dst[i]), p(self.volS), p(self.arms[i]), p(self.count[i]), D, H, W,
-                         iters, int(hp["cbca_distance"]), int(self.cbca_mode), p(self.cbca_ws), sp())
+                         iters, int(hp["cbca_distance"]), int(self.cbca_mode), sp())
             return cbca
 
         def make_sgm(vol):

@@ -31,7 +31,7 @@ __all__ = ["compute_features", "compute_cost_volume", "cost_volume_aggregation",
 #       from the reference only by float32 re-association (~1e-7 relative);
 #   1 = "exact": the reference's flat running sum over the whole region (pf:157-161), bit-identical
 #       to the reference, <= 729 additions per cell.
-CBCA_SEPARABLE, CBCA_EXACT, CBCA_SEPARABLE_TILED, CBCA_SEPARABLE_MARCH, CBCA_SEPARABLE_L2 = 0, 1, 2, 3, 4
+CBCA_SEPARABLE, CBCA_EXACT = 0, 1
 CBCA_MODE = CBCA_SEPARABLE
 
 
@@ -250,27 +250,16 @@ def compute_cross_region(image, intensity_threshold, distance_threshold):
     return _ret(region, image), _ret(count, image)
 
 
-def cbca_workspace(H, W):
-    """Per-tile halo table of the separable kernel (mccnn_cbca_workspace_bytes)."""
-    torch = _torch()
-    n = int(_ffi.lib().mccnn_cbca_workspace_bytes(int(H), int(W)))
-    return torch.empty((n + 3) // 4, dtype=torch.int32, device=_dev())
-
-
-def _cbca_one(hwd, D, arms, count, iters, dist, out=None, scratch=None, mode=None, workspace=None):
+def _cbca_one(hwd, D, arms, count, iters, dist, out=None, scratch=None, mode=None):
     H, W, _ = hwd.shape
     if out is None:
         out = _empty_hwd(H, W, D)
     if mode is None:
         mode = CBCA_MODE
-    if mode == CBCA_SEPARABLE_TILED and int(dist) > 14:     # the tiled kernel's halo is sized for match.py's distance (14)
-        mode = CBCA_SEPARABLE
     if scratch is None and iters >= 1:
         scratch = _empty_hwd(H, W, D)
-    if workspace is None and mode in (CBCA_SEPARABLE_TILED, CBCA_SEPARABLE_L2):
-        workspace = cbca_workspace(H, W)
     _ffi.call("mccnn_cbca", _ffi.ptr(hwd), _ffi.ptr(out), _ffi.ptr(scratch), _ffi.ptr(arms), _ffi.ptr(count),
-              D, int(H), int(W), int(iters), int(dist), int(mode), _ffi.ptr(workspace), _ffi.stream_ptr())
+              D, int(H), int(W), int(iters), int(dist), int(mode), _ffi.stream_ptr())
     return out
 
 

@@ -251,7 +251,6 @@ class SlabRank(object):
             self.colv = [reg(4, H, Wc, self.Dp), reg(5, H, Wc, self.Dp)]
         self.arms = [e(H, W, 4, dtype=torch.uint8), e(H, W, 4, dtype=torch.uint8)]
         self.count = [e(H, W, dtype=torch.int32), e(H, W, dtype=torch.int32)]
-        self.cbca_ws = _pf.cbca_workspace(H, W)
         ns = int(_ffi.lib().mccnn_sgm_scratch_bytes(H, W, D))
         self.sgm_flags = e((ns + 3) // 4, dtype=torch.int32)
         self.wta_local = e(4, H, W)                        # (disp L, min L, disp R, min R) of this slab
@@ -296,7 +295,8 @@ class SlabRank(object):
             call("mccnn_cross_arms", p(self.img[i]), p(self.arms[i]), p(self.count[i]), H, W,
                  ctypes.c_float(np.float32(hp["cbca_intensity"])), int(hp["cbca_distance"]), sp())
         it1 = int(hp["cbca_num_iterations1"])
-        if bases is None or it1 < 1 or int(hp["cbca_distance"]) > 255:
+        # the fused hand-over exists for the default summation order only: another mode aggregates in place and pushes
+        if bases is None or it1 < 1 or self.cbca_mode != _pf.CBCA_SEPARABLE:
             for v in range(2):
                 self._cbca(v, self.volA, self.volB, it1)
             if bases is not None:
@@ -312,7 +312,7 @@ class SlabRank(object):
     def _cbca(self, i, src, dst, iters):
         p, call, sp, hp, pl = _ffi.ptr, _ffi.call, _ffi.stream_ptr, self.hp, self.plan
         call("mccnn_cbca", p(src[i]), p(dst[i]), p(self.volS), p(self.arms[i]), p(self.count[i]), self.Dl, pl.H, pl.W,
-             iters, int(hp["cbca_distance"]), int(self.cbca_mode), p(self.cbca_ws), sp())
+             iters, int(hp["cbca_distance"]), int(self.cbca_mode), sp())
 
     def _views(self, flat, shapes):
         out, off = [], 0

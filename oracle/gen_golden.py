@@ -161,14 +161,94 @@ def gen_features():
     print("features_ckpt bytes", os.path.getsize(os.path.join(GOLDEN, "features_ckpt.npz")))
 
 
+def two_level_images(H, W, shift):
+    """Piece-wise constant pair: two grey levels split by a wavy vertical boundary, so that arms run to the
+    distance limit (13 pixels) almost everywhere and regions reach 27 x 27 = 729 (pf:585-599, :612-626)."""
+    hh, ww = np.mgrid[0:H, 0:W + shift]
+    q = (ww > (W + shift) / 2 + 4 * np.sin(hh / 3.0)).astype(np.float32) * 200.0 + 20.0
+    left, right = q[:, :W], q[:, shift:shift + W]
+    li = ((left - np.mean(left, axis=(0, 1))) / np.std(left, axis=(0, 1)))[..., None].astype(np.float32)
+    ri = ((right - np.mean(right, axis=(0, 1))) / np.std(right, axis=(0, 1)))[..., None].astype(np.float32)
+    return li, ri
+
+
+def gen_flat(pf):
+    """Worst-case cross regions (the other fixtures top out at 76 pixels): counts, the explicit list of one row band,
+    and the aggregation after 1, 2 and 5 rounds of a random volume, all from the reference's own code."""
+    H, W, D = 30, 64, 6
+    li, ri = two_level_images(H, W, 3)
+    rng = np.random.default_rng(404)
+    L = rng.standard_normal((D, H, W)).astype(np.float32)
+    R = rng.standard_normal((D, H, W)).astype(np.float32)
+    g = dict(left_image=li, right_image=ri, cv_L=L, cv_R=R)
+    reg, num = pf.compute_cross_region(li, 0.02, 14)
+    g["region_num_left"] = num
+    g["region_left_rows13_15"] = reg[13:15].astype(np.int16)
+    _, g["region_num_right"] = pf.compute_cross_region(ri, 0.02, 14)
+    for iters in (1, 2, 5):
+        a, b = pf.cost_volume_aggregation(li, ri, L, R, 0.02, 14, iters)
+        g["cbca%d_L" % iters], g["cbca%d_R" % iters] = a, b
+    np.savez_compressed(os.path.join(GOLDEN, "flat_regions.npz"), **g)
+    print("flat_regions: max region", int(num.max()), "mean", float(num.mean()), "bytes",
+          os.path.getsize(os.path.join(GOLDEN, "flat_regions.npz")))
+
+
+def gen_checkpoint_tensors():
+    """The ten conv tensors of the reference's shipped checkpoint (data/tensorboard_log/model_epoch2000.ckpt, read with
+    the product's CRC32C-verified bundle reader), so that real-weight features can be run on the GPU box, where
+    /root/reference does not exist (pf:32, :43), plus the float64 torch restatement's features of one image."""
+    spec = importlib.util.spec_from_file_location(
+        "mccnn_ckpt", os.path.join(ROOT, "mc-cnn-python_b200", "checkpoint.py"))
+    ck = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ck)
+    prefix = os.path.join(REFERENCE_ROOT, "data", "tensorboard_log", "model_epoch2000.ckpt")
+    ws, bs = ck.load_mccnn_weights(prefix)
+    g = {}
+    for i, (w, b) in enumerate(zip(ws, bs)):
+        g["conv%d_weights" % (i + 1)] = w
+        g["conv%d_biases" % (i + 1)] = b
+    np.savez_compressed(os.path.join(GOLDEN, "checkpoint_tensors.npz"), **g)
+    print("checkpoint_tensors bytes", os.path.getsize(os.path.join(GOLDEN, "checkpoint_tensors.npz")))
+
+
+def gen_file_formats():
+    """Bytes written by the reference's own util.py (py3-patched as oracle/stage_ref.py does: binary mode, header as
+    bytes): writePfm (util.py:54-70) of a small map incl. inf / NaN / negative values."""
+    import tempfile
+    import types
+    sys.path.insert(0, HERE)
+    import stage_ref
+    src = stage_ref._patch_util(open(os.path.join(REFERENCE_ROOT, "src", "util.py")).read())
+    util = types.ModuleType("reference_util")
+    exec(compile(src, "reference util.py", "exec"), util.__dict__)
+    rng = np.random.default_rng(9)
+    d = (rng.standard_normal((5, 7)) * 40).astype(np.float32)
+    d[0, 0], d[1, 2], d[4, 6] = np.inf, np.nan, -0.0
+    path = tempfile.mktemp(suffix=".pfm")
+    util.writePfm(d, path)
+    raw = np.frombuffer(open(path, "rb").read(), dtype=np.uint8)
+    back = util.readPfm(path)
+    os.remove(path)
+    np.savez_compressed(os.path.join(GOLDEN, "file_formats.npz"), pfm_map=d, pfm_bytes=raw, pfm_read_back=back)
+    print("file_formats bytes", os.path.getsize(os.path.join(GOLDEN, "file_formats.npz")))
+
+
 def main():
     os.makedirs(GOLDEN, exist_ok=True)
     pf = load_reference_pf()
+    if "--new" in sys.argv:          # only the fixtures added in round 2 (the others are unchanged)
+        gen_flat(pf)
+        gen_checkpoint_tensors()
+        gen_file_formats()
+        return
     # few grey levels -> long arms (large cross regions); many levels -> short arms
     gen_pipeline(pf, "pipeline_a", seed=101, H=20, W=40, D=8, levels=5, shift=2)
     gen_pipeline(pf, "pipeline_b", seed=202, H=33, W=29, D=11, levels=40, shift=3)
     gen_integer_cases(pf)
     gen_features()
+    gen_flat(pf)
+    gen_checkpoint_tensors()
+    gen_file_formats()
 
 
 if __name__ == "__main__":

@@ -70,3 +70,16 @@ def integer_golden():
 @pytest.fixture(scope="session")
 def features_golden():
     return load_golden("features_ckpt")
+
+
+@pytest.fixture(scope="session")
+def flat_golden():
+    """Two-level image (arms at the 13-pixel limit, regions up to 729) through the reference's own code."""
+    return load_golden("flat_regions")
+
+
+@pytest.fixture(scope="session")
+def checkpoint_golden():
+    """(weights, biases) of the reference's shipped checkpoint (ten conv tensors, oracle/gen_golden.py)."""
+    g = load_golden("checkpoint_tensors")
+    return [g["conv%d_weights" % i] for i in range(1, 6)], [g["conv%d_biases" % i] for i in range(1, 6)]

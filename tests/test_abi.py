@@ -50,7 +50,7 @@ def test_ctypes_table_mirrors_header(pkg):
 
 def test_no_compute_calls_without_gpu_but_pure_queries_work(pkg):
     lib = pkg._ffi.lib()
-    assert lib.mccnn_abi_version() == 1
+    assert lib.mccnn_abi_version() == 2
     for D in (1, 2, 3, 4, 11, 192, 400):
         assert lib.mccnn_dpitch(D) == pkg._ffi.dpitch(D) == (D + 3) // 4 * 4
     # two ping-pong activation maps + the hi/lo split weights of layers 2..5

@@ -75,6 +75,23 @@ def test_features_vs_golden_and_oracle(pf, pkg, oracle, features_golden):
     assert eq(net.features[0], fl)
 
 
+def test_features_with_the_shipped_checkpoint(pf, oracle, features_golden, checkpoint_golden):
+    """pf:32, :43: the reference restores model_epoch2000.ckpt; its ten conv tensors are a committed fixture, so the
+    CUDA net runs the REAL weights here: against the float64 torch restatement (golden) and the C oracle."""
+    g = features_golden
+    ws, bs = checkpoint_golden
+    img = g["image"]
+    fl, fr = pf.compute_features(img[..., None], img[:, ::-1].copy()[..., None], 11, 11, (ws, bs))
+    np.testing.assert_allclose(fl, g["features"], atol=FEAT_ATOL, rtol=0)
+    np.testing.assert_allclose(fr, oracle.net_forward(img[:, ::-1].copy(), ws, bs), atol=FEAT_ATOL, rtol=0)
+    np.testing.assert_allclose(np.linalg.norm(fl, axis=-1), 1.0, atol=1e-5)
+    # a larger, ragged image (several tiles per row band) with the real weights, against the oracle
+    rng = np.random.default_rng(8)
+    big = rng.standard_normal((70, 300)).astype(np.float32)
+    fb, _ = pf.compute_features(big[..., None], big[..., None], 11, 11, (ws, bs))
+    np.testing.assert_allclose(fb, oracle.net_forward(big, ws, bs), atol=FEAT_ATOL, rtol=0)
+
+
 # ------------------------------------------------------------------------------------------ cost volume
 def check_cost(got, ref):
     scale = float(np.abs(ref).max())
@@ -119,6 +136,27 @@ def test_cross_regions_vs_golden(pf, oracle, pipeline_golden):
     arms, count = pf.cross_arms(g["right_image"], 0.02, 14)
     ao, co = oracle.cross_arms(g["right_image"], 0.02, 14)
     assert eq(arms.cpu().numpy(), ao) and eq(count.cpu().numpy(), co)
+
+
+def test_flat_image_regions_and_aggregation_vs_golden(pf, flat_golden, monkeypatch):
+    """Worst case of pf:585-599 (arms at the 13-pixel limit, regions up to 729): counts, explicit list and the
+    aggregation against vectors from the reference's own code -- exact mode bit for bit, the separable mode within
+    the re-association tolerance."""
+    g = flat_golden
+    region, num = pf.compute_cross_region(g["left_image"], 0.02, 14)
+    assert num.max() == 729 and eq(num, g["region_num_left"])
+    assert eq(region[13:15], g["region_left_rows13_15"].astype(np.int32))
+    _, numr = pf.compute_cross_region(g["right_image"], 0.02, 14)
+    assert eq(numr, g["region_num_right"])
+    for iters in (1, 2, 5):
+        monkeypatch.setattr(pf, "CBCA_MODE", pf.CBCA_EXACT)
+        L, R = pf.cost_volume_aggregation(g["left_image"], g["right_image"], g["cv_L"], g["cv_R"], 0.02, 14, iters)
+        assert eq(L, g["cbca%d_L" % iters]) and eq(R, g["cbca%d_R" % iters]), iters
+        monkeypatch.setattr(pf, "CBCA_MODE", pf.CBCA_SEPARABLE)
+        Ls, Rs = pf.cost_volume_aggregation(g["left_image"], g["right_image"], g["cv_L"], g["cv_R"], 0.02, 14, iters)
+        scale = float(np.abs(g["cv_L"]).max())
+        np.testing.assert_allclose(Ls, g["cbca%d_L" % iters], atol=CBCA_SEP_RTOL * scale, rtol=0)
+        np.testing.assert_allclose(Rs, g["cbca%d_R" % iters], atol=CBCA_SEP_RTOL * scale, rtol=0)
 
 
 @pytest.fixture
@@ -183,86 +221,46 @@ def test_cbca_separable_vs_golden_and_oracle(pf, oracle, pipeline_golden):
     Lg, _ = pf.cost_volume_aggregation(li, ri, Li, Li, 0.02, 14, 1)
     Lo, _ = oracle.cost_volume_aggregation(li, ri, Li, Li, 0.02, 14, 1)
     assert eq(Lg, Lo)
-    # arms longer than the separable kernel's halo fall back to the flat walk, still correct
+    # arms longer than match.py's 13 pixels
     Lg, _ = pf.cost_volume_aggregation(li, ri, Li, Li, 0.02, 20, 1)
     Lo, _ = oracle.cost_volume_aggregation(li, ri, Li, Li, 0.02, 20, 1)
     assert eq(Lg, Lo)
 
 
-def test_cbca_tiled_tma_mode_matches_streaming_mode_and_oracle(pf, oracle, monkeypatch):
-    """MCCNN_CBCA_SEPARABLE_TILED (fused TMA-staged kernel) forms the same sums in the same order as the default
-    two-pass mode: identical results, and both within the re-association tolerance of the oracle.  Covers flat
-    images (13-pixel arms: sub-slab fallback levels), ragged sizes, small and odd granule counts."""
-    for (H, W, D, levels, iters) in [(40, 90, 70, 4, 3), (33, 47, 192, 30, 2), (37, 29, 5, 1, 2), (50, 21, 33, 2, 3),
-                                      (64, 64, 12, 1, 1), (17, 200, 9, 3, 2)]:
+def test_cbca_separable_many_shapes_vs_oracle(pf, oracle):
+    """Default mode against the C oracle (pinned to the reference) within the re-association tolerance: flat images
+    (13-pixel arms everywhere), widths around the 4-pixel patch and 64-pixel lines, granule counts that are not a
+    multiple of 16, images shorter than an arm, one to five rounds, distance thresholds other than match.py's 14."""
+    cases = [(40, 90, 70, 4, 3, 14), (33, 47, 192, 30, 2, 14), (9, 29, 33, 1, 2, 14), (50, 21, 40, 2, 3, 14),
+             (64, 64, 32, 1, 1, 14), (17, 200, 29, 3, 2, 14), (70, 40, 100, 2, 2, 14), (12, 129, 8, 1, 4, 14),
+             (25, 300, 20, 1, 5, 14), (31, 191, 68, 2, 3, 20), (14, 140, 12, 1, 2, 40), (20, 65, 6, 1, 3, 3),
+             (5, 64, 4, 2, 2, 1), (3, 128, 130, 1, 2, 14)]
+    for (H, W, D, levels, iters, dist) in cases:
         li, ri = synth_images(H * W + D, H, W, levels, 2)
         rng = np.random.default_rng(D)
         Lv = rng.standard_normal((D, H, W)).astype(np.float32) * 50
         Rv = rng.standard_normal((D, H, W)).astype(np.float32) * 50
-        monkeypatch.setattr(pf, "CBCA_MODE", pf.CBCA_SEPARABLE)
-        Ls, Rs = pf.cost_volume_aggregation(li, ri, Lv, Rv, 0.02, 14, iters)
-        monkeypatch.setattr(pf, "CBCA_MODE", pf.CBCA_SEPARABLE_TILED)
-        Lt, Rt = pf.cost_volume_aggregation(li, ri, Lv, Rv, 0.02, 14, iters)
-        assert eq(Ls, Lt) and eq(Rs, Rt), (H, W, D)
-        Lo, Ro = oracle.cost_volume_aggregation(li, ri, Lv, Rv, 0.02, 14, iters)
+        Lt, Rt = pf.cost_volume_aggregation(li, ri, Lv, Rv, 0.02, dist, iters)
+        Lo, Ro = oracle.cost_volume_aggregation(li, ri, Lv, Rv, 0.02, dist, iters)
         scale = float(np.abs(Lo).max())
-        np.testing.assert_allclose(Lt, Lo, atol=CBCA_SEP_RTOL * scale, rtol=0)
+        np.testing.assert_allclose(Lt, Lo, atol=CBCA_SEP_RTOL * scale, rtol=0, err_msg=str((H, W, D, levels, iters, dist)))
         np.testing.assert_allclose(Rt, Ro, atol=CBCA_SEP_RTOL * scale, rtol=0)
 
 
-def test_cbca_march_mode_matches_streaming_mode_and_oracle(pf, oracle, monkeypatch):
-    """MCCNN_CBCA_SEPARABLE_MARCH (one row-marching TMA kernel per round) forms the same sums in the same order
-    as the two streaming passes: identical results for every strip shape and row segmentation, and within the
-    re-association tolerance of the oracle.  Covers flat images (13-pixel arms: full halo boxes), ragged widths,
-    granule counts that are not a multiple of the strip's 8, images shorter than an arm, several row segments."""
-    cases = [(40, 90, 70, 4, 3), (33, 47, 192, 30, 2), (9, 29, 33, 1, 2), (50, 21, 40, 2, 3), (64, 64, 32, 1, 1),
-             (17, 200, 29, 3, 2), (70, 40, 100, 2, 2)]
-    for ci, (H, W, D, levels, iters) in enumerate(cases):
-        li, ri = synth_images(H * W + D, H, W, levels, 2)
-        rng = np.random.default_rng(D)
-        Lv = rng.standard_normal((D, H, W)).astype(np.float32) * 50
-        Rv = rng.standard_normal((D, H, W)).astype(np.float32) * 50
-        monkeypatch.setattr(pf, "CBCA_MODE", pf.CBCA_SEPARABLE)
-        monkeypatch.delenv("MCCNN_CBCA_MARCH", raising=False)
-        Ls, Rs = pf.cost_volume_aggregation(li, ri, Lv, Rv, 0.02, 14, iters)
-        monkeypatch.setattr(pf, "CBCA_MODE", pf.CBCA_SEPARABLE_MARCH)
-        Lt, Rt = pf.cost_volume_aggregation(li, ri, Lv, Rv, 0.02, 14, iters)
-        assert eq(Ls, Lt) and eq(Rs, Rt), (H, W, D)
-        for variant in range(6):
-            for nseg in ((1, 3) if ci % 2 else (2, 5)):
-                monkeypatch.setenv("MCCNN_CBCA_MARCH", "%d,%d" % (variant, nseg))
-                Lt, Rt = pf.cost_volume_aggregation(li, ri, Lv, Rv, 0.02, 14, iters)
-                assert eq(Ls, Lt) and eq(Rs, Rt), (H, W, D, variant, nseg)
-        monkeypatch.delenv("MCCNN_CBCA_MARCH", raising=False)
-        Lo, Ro = oracle.cost_volume_aggregation(li, ri, Lv, Rv, 0.02, 14, iters)
-        scale = float(np.abs(Lo).max())
-        np.testing.assert_allclose(Lt, Lo, atol=CBCA_SEP_RTOL * scale, rtol=0)
-        np.testing.assert_allclose(Rt, Ro, atol=CBCA_SEP_RTOL * scale, rtol=0)
-    # shapes the marching kernel is not built for fall back to the streaming passes (still correct)
-    Li = rng.integers(0, 64, (12, 30, 44)).astype(np.float32)
-    li, ri = synth_images(5, 30, 44, 3, 1)
-    for dist in (14, 20):
-        Lg, _ = pf.cost_volume_aggregation(li, ri, Li, Li, 0.02, dist, 2)
-        Lo, _ = oracle.cost_volume_aggregation(li, ri, Li, Li, 0.02, dist, 2)
-        np.testing.assert_allclose(Lg, Lo, atol=CBCA_SEP_RTOL * 64, rtol=0)
-
-
-def test_cbca_l2_mode_matches_streaming_mode(pf, monkeypatch):
-    """MCCNN_CBCA_SEPARABLE_L2 (both passes in one persistent, band-pipelined kernel, row sums in a 64-row ring)
-    is the same arithmetic as the two streaming passes: identical bits, for images taller than the ring (ring rows
-    reused), shorter than a band, ragged widths / granule counts, flat images (13-row arms across bands)."""
-    cases = [(150, 90, 70, 4, 3), (200, 47, 192, 30, 2), (9, 29, 33, 1, 2), (70, 21, 40, 2, 3), (64, 64, 32, 1, 1),
-             (137, 200, 29, 3, 2), (5, 40, 100, 2, 2)]
-    for (H, W, D, levels, iters) in cases:
-        li, ri = synth_images(H * W + D, H, W, levels, 2)
-        rng = np.random.default_rng(D)
-        Lv = rng.standard_normal((D, H, W)).astype(np.float32) * 50
-        Rv = rng.standard_normal((D, H, W)).astype(np.float32) * 50
-        monkeypatch.setattr(pf, "CBCA_MODE", pf.CBCA_SEPARABLE)
-        Ls, Rs = pf.cost_volume_aggregation(li, ri, Lv, Rv, 0.02, 14, iters)
-        monkeypatch.setattr(pf, "CBCA_MODE", pf.CBCA_SEPARABLE_L2)
-        Lt, Rt = pf.cost_volume_aggregation(li, ri, Lv, Rv, 0.02, 14, iters)
-        assert eq(Ls, Lt) and eq(Rs, Rt), (H, W, D)
+def test_cbca_every_mode_with_long_arms(pf, oracle, monkeypatch):
+    """distance_threshold 20 (arms up to 19 pixels, longer than match.py's 13) on a flat image, every mode, integer
+    costs: exact sums, so every mode must equal the oracle bit for bit after one round."""
+    rng = np.random.default_rng(3)
+    Li = rng.integers(0, 64, (12, 30, 90)).astype(np.float32)
+    li, ri = synth_images(5, 30, 90, 1, 1)
+    Lo, _ = oracle.cost_volume_aggregation(li, ri, Li, Li, 0.02, 20, 1)
+    for mode in (pf.CBCA_SEPARABLE, pf.CBCA_EXACT):
+        monkeypatch.setattr(pf, "CBCA_MODE", mode)
+        Lg, _ = pf.cost_volume_aggregation(li, ri, Li, Li, 0.02, 20, 1)
+        assert eq(Lg, Lo), mode
+        L2, _ = pf.cost_volume_aggregation(li, ri, Li, Li, 0.02, 20, 2)
+        Lo2, _ = oracle.cost_volume_aggregation(li, ri, Li, Li, 0.02, 20, 2)
+        np.testing.assert_allclose(L2, Lo2, atol=CBCA_SEP_RTOL * 64, rtol=0)
 
 
 def test_cbca_plane_constant_is_fixed_point(pf):

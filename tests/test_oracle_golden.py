@@ -99,6 +99,30 @@ def test_integer_cost_cases(oracle, integer_golden):
     assert eq(oracle.bilateral_filter(g["left_image"], g["half_median"], 5, 5, 0, 6, 2), g["half_bilateral"])
 
 
+def test_flat_image_regions_and_aggregation(oracle, flat_golden):
+    """Worst case of pf:585-599: arms at the distance limit, regions of up to 27 x 27 = 729 pixels."""
+    g = flat_golden
+    region, num = oracle.compute_cross_region(g["left_image"], 0.02, 14)
+    assert num.max() == 729 and num.mean() > 400
+    assert eq(num, g["region_num_left"])
+    assert eq(region[13:15], g["region_left_rows13_15"].astype(np.int32))
+    _, numr = oracle.compute_cross_region(g["right_image"], 0.02, 14)
+    assert eq(numr, g["region_num_right"])
+    for iters in (1, 2, 5):
+        L, R = oracle.cost_volume_aggregation(g["left_image"], g["right_image"], g["cv_L"], g["cv_R"], 0.02, 14, iters)
+        assert eq(L, g["cbca%d_L" % iters]) and eq(R, g["cbca%d_R" % iters]), iters
+
+
+def test_feature_net_on_the_shipped_checkpoint(oracle, features_golden, checkpoint_golden):
+    """The C restatement of model.py:40-64 with the reference's real weights against the float64 torch restatement."""
+    g = features_golden
+    ws, bs = checkpoint_golden
+    assert eq(ws[0], g["conv1_weights"]) and eq(bs[0], g["conv1_biases"]) and eq(bs[4], g["conv5_biases"])
+    np.testing.assert_allclose([float(w.astype(np.float64).sum()) for w in ws], g["weight_sums"], rtol=0, atol=1e-9)
+    f = oracle.net_forward(g["image"], ws, bs)
+    np.testing.assert_allclose(f, g["features"], atol=2e-6, rtol=0)
+
+
 def test_feature_net_matches_torch_restatement(oracle, features_golden):
     g = features_golden
     ws, bs = oracle.glorot_uniform_weights(seed=int(g["glorot_seed"]))

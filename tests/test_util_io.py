@@ -52,3 +52,16 @@ def test_pgm_and_time_file(tmp_path):
     assert os.path.isdir(str(tmp_path / "a" / "b" / "c"))
     g = util.normal(0, 6)
     assert abs(g(0.0) - 1.0 / (np.sqrt(2 * np.pi) * 6)) < 1e-12
+
+
+def test_pfm_bytes_equal_the_reference_writer(tmp_path):
+    """tests/golden/file_formats.npz holds the bytes the reference's own util.writePfm (util.py:54-70, run through
+    oracle/gen_golden.py) wrote for a map with inf / NaN / -0.0: the drop-in writer must produce the same file, and
+    the drop-in reader the same array the reference's readPfm (util.py:6-25) returned."""
+    g = np.load(os.path.join(ROOT, "tests", "golden", "file_formats.npz"))
+    path = str(tmp_path / "g.pfm")
+    util.writePfm(g["pfm_map"], path)
+    assert open(path, "rb").read() == g["pfm_bytes"].tobytes()
+    back = util.readPfm(path)
+    assert np.array_equal(back, g["pfm_read_back"], equal_nan=True)
+    assert np.array_equal(back.view(np.uint32), g["pfm_map"].view(np.uint32))      # bit for bit incl. NaN payload, -0.0
