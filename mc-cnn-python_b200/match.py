@@ -103,7 +103,8 @@ def main(argv=None):
         import torch.distributed as dist
         import slab                                                                # this directory's slab.py
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        if not dist.is_initialized():
+        own_group = not dist.is_initialized()
+        if own_group:
             dist.init_process_group("nccl", device_id=torch.device("cuda", torch.cuda.current_device()))
         lo, hi = 0, max(last - first + 1, 0)                                       # every rank works on every pair
     else:
@@ -148,6 +149,10 @@ def main(argv=None):
         print("{}: rank {} pair {} ({}x{}x{}) matched in {:.4f} s -> {}".format(datetime.now(), rank, index, height, width,
                                                                                 ndisp, elapsed, res_dir))
         done.append(index)
+    if slab_mode and own_group:
+        torch.cuda.synchronize()
+        dist.barrier()
+        dist.destroy_process_group()
     return done
 
 

@@ -312,8 +312,10 @@ def semi_global_matching(left_image, right_image, cost_volume, r, sgm_P1, sgm_P2
 def SGM_average(left_cost_volume, right_cost_volume, left_image, right_image,
                 sgm_P1, sgm_P2, sgm_Q1, sgm_Q2, sgm_D, sgm_V):
     """pf:187.  Four chained in-place passes per volume, (0,1) (0,-1) (-1,0) (1,0) (pf:194-208); the
-    reference's closing (X+X+X+X)/4. is the identity.  HWD-view tensors are
-    updated in place like the reference's arrays; NumPy / DHW inputs are not written back."""
+    reference's closing (X+X+X+X)/4. is the identity.  Like the reference (pf:195-232) the
+    volumes handed in are MUTATED -- they hold the chained passes' result afterwards -- and the returned volumes are
+    equal to them: NumPy arrays are written back and fresh arrays returned; HWD-view tensors are updated in place
+    (the returned views alias them, zero copy); DHW tensors are written back."""
     li, ri = _image2d(left_image), _image2d(right_image)
     hl, D, H, W = _as_hwd(left_cost_volume)
     hr, D2, H2, W2 = _as_hwd(right_cost_volume)
@@ -322,7 +324,13 @@ def SGM_average(left_cost_volume, right_cost_volume, left_image, right_image,
     _ffi.call("mccnn_sgm_average_pair", _ffi.ptr(hl), _ffi.ptr(hr), _ffi.ptr(li), _ffi.ptr(ri),
               _ffi.ptr(flags), D, H, W, float(sgm_P1), float(sgm_P2), float(sgm_Q1), float(sgm_Q2),
               float(sgm_D), float(sgm_V), _ffi.stream_ptr())
-    return _ret_volume(hl, D, left_cost_volume), _ret_volume(hr, D, right_cost_volume)
+    outs = _ret_volume(hl, D, left_cost_volume), _ret_volume(hr, D, right_cost_volume)
+    for given, out in zip((left_cost_volume, right_cost_volume), outs):
+        if isinstance(given, np.ndarray):
+            np.copyto(given, out)                                 # the reference's in-place passes (pf:544)
+        elif _is_tensor(given) and not _is_hwd_view(given):
+            given.copy_(out)
+    return outs
 
 
 # ------------------------------------------------------------------------------------------ a8

@@ -171,10 +171,22 @@ class DistComm(object):
 
     def make_arenas(self, nfloats):
         """The arena peers write into: symmetric memory (same size on every rank), mapped into every rank's address
-        space over NVLink by the rendezvous."""
+        space over NVLink by the rendezvous.  The allocation is local and may fail on some ranks only; the rendezvous
+        is collective.  So the ranks vote after the allocation and enter the rendezvous only if every one of them
+        succeeded -- otherwise all raise together (a rank that failed alone would leave the others blocked in the
+        rendezvous)."""
         import torch
-        import torch.distributed._symmetric_memory as symm_mem
-        self.arena = symm_mem.empty(int(nfloats), dtype=torch.float32, device=torch.device("cuda", torch.cuda.current_device()))
+        ok, why, arena, symm_mem = 1, "", None, None
+        try:
+            import torch.distributed._symmetric_memory as symm_mem
+            arena = symm_mem.empty(int(nfloats), dtype=torch.float32, device=torch.device("cuda", torch.cuda.current_device()))
+        except (ImportError, AttributeError, RuntimeError) as e:
+            ok, why = 0, repr(e)
+        flag = torch.tensor([ok], dtype=torch.int32, device="cuda")
+        self.dist.all_reduce(flag, op=self.dist.ReduceOp.MIN)
+        if int(flag.item()) == 0:
+            raise RuntimeError("symmetric memory unavailable: %s" % (why or "on another rank"))
+        self.arena = arena
         self.symm = symm_mem.rendezvous(self.arena, self.dist.group.WORLD)
         return [self.arena]
 
@@ -584,17 +596,12 @@ class SlabMatcher(object):
         if transport == "p2p":
             # symmetric memory is a young torch API: every rank tries, and all fall back to the staged NCCL
             # transport together if any of them cannot map its peers (still GPU to GPU, never through the host)
-            import torch
-            ok, why = 1, ""
+            # (make_arenas votes before its collective step, so it raises on every rank or on none)
             try:
                 arena = self.comm.make_arenas(6 * self.plan.region_floats())[0]
-            except (ImportError, AttributeError, RuntimeError) as e:
-                ok, why, arena = 0, repr(e), None
-            flag = torch.tensor([ok], dtype=torch.int32, device="cuda")
-            self.comm.dist.all_reduce(flag, op=self.comm.dist.ReduceOp.MIN)
-            if int(flag.item()) == 0:
+            except RuntimeError as e:
                 if self.comm.rank == 0:
-                    print("slab: peer-memory transport unavailable (%s); using staged NCCL exchanges" % (why or "on another rank"))
+                    print("slab: peer-memory transport unavailable (%s); using staged NCCL exchanges" % e)
                 arena, transport = None, "nccl"
                 self.transport = transport
         self.rank = SlabRank(self.plan, self.comm.rank, checkpoint=checkpoint, arena=arena, **hp)

@@ -298,9 +298,12 @@ def test_sgm_integer_costs_exact(pf, integer_golden):
 def test_sgm_average_is_four_chained_passes(pf, pipeline_golden):
     import torch
     g = pipeline_golden
-    L, R = pf.SGM_average(g["cbca1_L"].copy(), g["cbca1_R"].copy(), g["left_image"], g["right_image"],
-                          2.3, 55.9, 4, 8, 0.08, 1.5)
+    xl, xr = g["cbca1_L"].copy(), g["cbca1_R"].copy()
+    L, R = pf.SGM_average(xl, xr, g["left_image"], g["right_image"], 2.3, 55.9, 4, 8, 0.08, 1.5)
     assert eq(L, g["sgm_L"]) and eq(R, g["sgm_R"])
+    # the reference's passes run in place (pf:195-232, :544): the arrays handed in hold the result afterwards, and
+    # what is returned is a different object (pf:232 builds a new array)
+    assert eq(xl, g["sgm_L"]) and eq(xr, g["sgm_R"]) and L is not xl and R is not xr
     # tensor path: HWD views are updated in place and returned
     hl, D, _, _ = pf._as_hwd(torch.from_numpy(g["cbca1_L"]).cuda())
     hr, _, _, _ = pf._as_hwd(torch.from_numpy(g["cbca1_R"]).cuda())
@@ -457,8 +460,9 @@ def test_pipeline_object_matches_stagewise_functions_and_oracle(pkg, pf, oracle,
     # volume agrees to scale-relative 1e-4 and the disparity map agrees except for rare near-tie flips
     scale = float(np.abs(g["cbca2_L"]).max())
     np.testing.assert_allclose(L, g["cbca2_L"], atol=1e-4 * scale, rtol=0)
-    agree = np.mean(np.abs(d - g["bilateral"]) < 1e-3)
-    assert agree >= 0.97, agree
+    flips = int(np.sum(np.abs(d - g["bilateral"]) >= 1e-3))
+    print("pipeline object vs reference golden: %d of %d pixels differ by >= 1e-3" % (flips, d.size))
+    assert flips <= max(1, d.size // 1000), flips
 
 
 def test_full_pipeline_recovers_known_shift(pkg):
@@ -514,7 +518,9 @@ def test_config1_full_pipeline_stagewise_vs_oracle(pkg, pf, oracle):
     np.testing.assert_allclose(d, st["bilateral"], rtol=2e-6, atol=1e-6)
     # end to end (everything on the GPU, CUDA features): the maps agree except for rare near-tie flips
     d2 = pkg.match_pair(li, ri, D, checkpoint=(ws, bs))
-    assert np.mean(np.abs(d2 - do) < 1e-3) > 0.97
+    flips = int(np.sum(np.abs(d2 - do) >= 1e-3))
+    print("config 1 end to end: %d of %d pixels differ from the oracle's final map by >= 1e-3" % (flips, d2.size))
+    assert flips <= d2.size // 1000, flips
 
 
 def test_config2_cost_volume_and_wta_vs_oracle(pf, oracle):
@@ -532,28 +538,6 @@ def test_config2_cost_volume_and_wta_vs_oracle(pf, oracle):
     assert eq(dl, dlo) and eq(dr, dro)
     dl2, _ = pf.disparity_prediction(L, R)
     assert np.mean(dl2 == dlo) > 0.999
-
-
-def test_config3_full_size_properties(pkg):
-    """BASELINE config 3 size (1024x1024x192): size-independent properties of the whole pipeline object --
-    a pair shifted by a known disparity is recovered, and the run is deterministic (two runs are bit-identical)."""
-    import torch
-    H, W, D, shift = 1024, 1024, 192, 21
-    rng = np.random.default_rng(3)
-    base = rng.random((H, W + shift)).astype(np.float32)
-    k = np.ones(5, np.float32) / 5
-    base = np.apply_along_axis(lambda v: np.convolve(v, k, mode="same"), 1, base)
-    q = np.floor(base / base.max() * 255)
-    left, right = q[:, :W], q[:, shift:]
-    li = ((left - left.mean()) / left.std())[..., None].astype(np.float32)
-    ri = ((right - right.mean()) / right.std())[..., None].astype(np.float32)
-    m = pkg.StereoMatcher(H, W, D)
-    m.set_images(li, ri)
-    d1 = m.run().clone()
-    d2 = m.run().clone()
-    assert torch.equal(d1, d2)
-    inner = d1[16:-16, D:-16].cpu().numpy()
-    assert np.mean(np.abs(inner - shift) < 0.5) > 0.95, float(np.mean(np.abs(inner - shift) < 0.5))
 
 
 # ------------------------------------------------------------------------------------------ match.py drop-in
