@@ -61,8 +61,8 @@ __global__ void __launch_bounds__(256) k_conv1(const float *__restrict__ img, co
 // three horizontal taps are the same rows read through descriptors whose start address is shifted by
 // 0 / 1 / 2 pixels (the 128B swizzle is a function of the absolute shared-memory address, so a start that
 // is not 1024-byte aligned needs no base offset -- checked on the device), which is why a tile yields 126
-// pixels, not 128.  Consecutive tiles visit the channel blocks in opposite order, so the weights are
-// reloaded once per tile, not twice.  An input row feeds up to three output rows (one per kernel row); the
+// pixels, not 128.  Tiles are taken in pairs, block 0 of both then block 1 of both, so the weights are
+// reloaded once per tile, not twice, and the accumulation order is the same for every tile.  An input row feeds up to three output rows (one per kernel row); the
 // weights of a kernel column are stacked by kernel row in shared memory and the accumulators of consecutive
 // output rows are adjacent in TMEM, so ONE tcgen05.mma with N = 64 / 128 / 192 updates all of them -- small-N
 // MMAs do not run proportionally faster, so this halves the MMA count and the time.  Accumulators are zeroed
@@ -131,18 +131,21 @@ k_conv64_tc(const __grid_constant__ CtcMaps maps, const float *__restrict__ bias
     const unsigned idesc_base = (1u << 4) | (2u << 7) | (2u << 10) | ((unsigned)(128 >> 4) << 24);
     constexpr int NROW = CT_ROWS + 2;           // input rows per tile
 
-    // A tile visits the channel blocks in the order (t & 1), (t & 1) ^ 1, so the block the previous tile ended with
-    // is still resident.  Row steps are numbered globally: rr = (tile ordinal * 2 + block ordinal) * NROW + r.
+    // A CTA takes its tiles two at a time (one per accumulator buffer) and visits  block 0 of both, then block 1 of both:
+    // the weights are reloaded once per tile on average, and EVERY tile accumulates block 0 before block 1 -- a pixel's
+    // features do not depend on where its tile falls in some CTA's sequence, so a row band of an image (slab.py) gives
+    // the bits of the whole image.  Row steps are numbered globally in that order.
     if (warp == 1) {
         // ================= TMA producer (one lane) =================
         if (lane == 0) {
             unsigned rr = 0, wloads = 0;
             int resident = -1;
-            unsigned tt = 0;
-            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, tt++) {
-                const int ty = tile / ntx, y0 = ty * CT_ROWS, x0 = (tile - ty * ntx) * CT_PIX;
-                for (int bi = 0; bi < 2; bi++) {
-                    const int kb = (tt & 1) ^ bi;
+            for (int tile0 = blockIdx.x; tile0 < ntiles; tile0 += 2 * gridDim.x) {
+              for (int kb = 0; kb < 2; kb++) {
+                for (int mem = 0; mem < 2; mem++) {
+                    const int tile = tile0 + mem * gridDim.x;
+                    if (tile >= ntiles) break;
+                    const int ty = tile / ntx, y0 = ty * CT_ROWS, x0 = (tile - ty * ntx) * CT_PIX;
                     if (kb != resident) {
                         // every MMA issued so far reads the resident weights: wait for the last row step
                         if (rr > 0) {
@@ -167,16 +170,19 @@ k_conv64_tc(const __grid_constant__ CtcMaps maps, const float *__restrict__ bias
                         tc_tma_load_3d(sm.a_hi[rr & 1], &maps.in, kb * 32, x0, y0 + r, &sm.bar_row[rr & 1]);
                     }
                 }
+              }
             }
         }
     } else if (warp < 8) {
         // ================= operand split (warps 2-7) and MMA issue (warp 0, lane 0) =================
-        unsigned rr = 0, wloads = 0, tt = 0;
+        unsigned rr = 0, wloads = 0, pair = 0;
         int resident = -1;
-        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, tt++) {
-            const unsigned abuf = tt & 1;
-            for (int bi = 0; bi < 2; bi++) {
-                const int kb = (tt & 1) ^ bi;
+        for (int tile0 = blockIdx.x; tile0 < ntiles; tile0 += 2 * gridDim.x, pair++) {
+          for (int kb = 0; kb < 2; kb++) {
+            for (int mem = 0; mem < 2; mem++) {
+                if (tile0 + mem * (int)gridDim.x >= ntiles) break;
+                const unsigned abuf = mem, tt = 2 * pair + mem;
+                const int bi = kb;
                 bool new_weights = false;
                 if (kb != resident) { new_weights = true; resident = kb; }
                 for (int r = 0; r < NROW; r++, rr++) {
@@ -220,6 +226,7 @@ k_conv64_tc(const __grid_constant__ CtcMaps maps, const float *__restrict__ bias
                 }
                 if (new_weights) wloads++;
             }
+          }
         }
     } else {
         // ================= epilogue (warps 8-15): two warps per TMEM lane quarter, two output rows each =================

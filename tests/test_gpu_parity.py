@@ -92,6 +92,26 @@ def test_features_with_the_shipped_checkpoint(pf, oracle, features_golden, check
     np.testing.assert_allclose(fb, oracle.net_forward(big, ws, bs), atol=FEAT_ATOL, rtol=0)
 
 
+def test_features_of_a_row_band_are_the_bits_of_the_whole_image(pf):
+    """The net is local (11x11 receptive field), so rows [lo, hi) of the features need image rows [lo-5, hi+5) only --
+    what the row-band feature exchange of the slab partition relies on.  The tensor-core layers must also give the SAME
+    BITS for a band as for the whole image: every tile accumulates the two input-channel blocks in the same order
+    wherever it falls in a CTA's sequence (round 1 alternated the order per tile ordinal: 1e-6 differences at sizes
+    with many tiles per CTA, found by the slab parity leg of bench.py)."""
+    import torch
+    rng = np.random.default_rng(12)
+    H, W = 700, 1500
+    img = torch.from_numpy(rng.standard_normal((H, W)).astype(np.float32)).cuda()
+    ws, bs = pf.glorot_uniform_weights(seed=0)
+    full, _ = pf.compute_features(img[..., None], img[..., None], 11, 11, (ws, bs))
+    for lo, hi in ((0, 130), (129, 402), (350, 700), (333, 334)):
+        a, b = max(lo - 5, 0), min(hi + 5, H)
+        band, _ = pf.compute_features(img[a:b, :, None], img[a:b, :, None], 11, 11, (ws, bs))
+        # (rows of the band whose 5-row halo was cut by the band's own zero padding are not comparable)
+        top, bot = (5 if a > 0 else 0), (5 if b < H else 0)
+        assert torch.equal(band[top:band.shape[0] - bot], full[a + top:b - bot]), (lo, hi)
+
+
 # ------------------------------------------------------------------------------------------ cost volume
 def check_cost(got, ref):
     scale = float(np.abs(ref).max())

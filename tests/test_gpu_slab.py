@@ -53,7 +53,8 @@ def test_copy3d_packs_and_unpacks_blocks(pkg):
     assert torch.equal(back[:, :, 4:16], src[:, :, 4:16]) and float(back[:, :, :4].abs().sum()) == 0.0
 
 
-@pytest.mark.parametrize("H,W,D,world", [(40, 96, 48, 2), (33, 75, 37, 3), (48, 130, 100, 4), (21, 64, 31, 8)])
+@pytest.mark.parametrize("H,W,D,world", [(40, 96, 48, 2), (33, 75, 37, 3), (48, 130, 100, 4), (21, 64, 31, 8),
+                                         (420, 1300, 200, 2), (300, 900, 96, 3)])
 def test_slab_partition_equals_single_gpu_pipeline(pkg, H, W, D, world):
     """The partitioned pipeline returns the single-GPU pipeline's disparity map bit for bit, and so do its
     intermediate volumes (every cell is computed by the same kernel on the same operands, only elsewhere)."""
