@@ -9,6 +9,8 @@
 // 16 B granule of the neighbour pixel's disparity row (fully coalesced for any region shape).
 #include "common.cuh"
 #include "cbca_stream.cuh"
+#include "cbca_chain.cuh"
+#include <stdlib.h>
 
 namespace mccnn {
 
@@ -126,9 +128,9 @@ static int stream_round(const float *src, float *scratch, float *out, const CsSc
     return MCCNN_OK;
 }
 
-// n >= 1 rounds; every round reads the previous round's `out`; the last column pass may scatter
-static int separable_rounds(const float *in, float *out, float *scratch, const CsScatter *sc, const uint8_t *arms,
-                            const int32_t *count, int G, int H, int W, int iters, cudaStream_t s) {
+// n >= 1 rounds as two streaming passes each; every round reads the previous round's `out`; the last column pass may scatter
+static int two_pass_rounds(const float *in, float *out, float *scratch, const CsScatter *sc, const uint8_t *arms,
+                           const int32_t *count, int G, int H, int W, int iters, cudaStream_t s) {
     const float *src = in;
     for (int it = 0; it < iters; it++) {
         int rc = stream_round(src, scratch, out, (sc && it + 1 == iters) ? sc : nullptr, arms, count, G, H, W, s);
@@ -136,6 +138,54 @@ static int separable_rounds(const float *in, float *out, float *scratch, const C
         src = out;
     }
     return MCCNN_OK;
+}
+
+static int launch_colrow(const float *hs_in, float *hs_out, const uint8_t *arms, const int32_t *count, int G, int H, int W, int hm,
+                         cudaStream_t s) {
+    const size_t smem = cc_smem_bytes(hm);
+    // per device and cheap: set on every launch rather than cached in a process-wide static
+    MCCNN_CUDA(cudaFuncSetAttribute(k_cbca_colrow, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid(cdiv(G, CS_GC), cdiv(W, CC_S), H);
+    k_cbca_colrow<<<grid, CC_THREADS, smem, s>>>(reinterpret_cast<const float4 *>(hs_in), reinterpret_cast<float4 *>(hs_out),
+                                                 reinterpret_cast<const uchar4 *>(arms), count, G, H, W, hm);
+    MCCNN_LAUNCHED("cbca_colrow");
+    return MCCNN_OK;
+}
+
+// n >= 2 rounds, chained: rows | (n-1) x colrow | cols.  The row sums ping-pong between `out` and `scratch` so that
+// the last ones sit in `scratch` and the closing column pass can write `out` (or scatter, sc != NULL).
+static int chained_rounds(const float *in, float *out, float *scratch, const CsScatter *sc, const uint8_t *arms,
+                          const int32_t *count, int G, int H, int W, int iters, int hm, cudaStream_t s) {
+    dim3 grid(cdiv(G, CS_GC), cdiv(W, CS_PW), cdiv(H, CS_PH));
+    float *hs[2];
+    hs[(iters - 1) & 1] = scratch;
+    hs[iters & 1] = out;
+    k_cbca_pass<false, CS_ITEMS, 1><<<grid, CS_THREADS, 0, s>>>(reinterpret_cast<const float4 *>(in), reinterpret_cast<float4 *>(hs[0]),
+                                                                reinterpret_cast<const uchar4 *>(arms), count, G, H, W);
+    MCCNN_LAUNCHED("cbca_rows");
+    for (int k = 1; k < iters; k++) {
+        int rc = launch_colrow(hs[(k - 1) & 1], hs[k & 1], arms, count, G, H, W, hm, s);
+        if (rc) return rc;
+    }
+    if (!sc) {
+        k_cbca_pass<true, CS_ITEMS, 1><<<grid, CS_THREADS, 0, s>>>(reinterpret_cast<const float4 *>(scratch), reinterpret_cast<float4 *>(out),
+                                                                   reinterpret_cast<const uchar4 *>(arms), count, G, H, W);
+        MCCNN_LAUNCHED("cbca_cols");
+    } else {
+        k_cbca_pass<true, CS_ITEMS, 1, true><<<grid, CS_THREADS, 0, s>>>(reinterpret_cast<const float4 *>(scratch), nullptr,
+                                                                         reinterpret_cast<const uchar4 *>(arms), count, G, H, W, *sc);
+        MCCNN_LAUNCHED("cbca_cols_scatter");
+    }
+    return MCCNN_OK;
+}
+
+// MCCNN_CBCA_CHAIN=1 (tuning / cross-check) selects the chained rounds; the default is two streaming passes per round
+static int separable_rounds(const float *in, float *out, float *scratch, const CsScatter *sc, const uint8_t *arms,
+                            const int32_t *count, int G, int H, int W, int iters, int hm, cudaStream_t s) {
+    const char *e = getenv("MCCNN_CBCA_CHAIN");
+    const bool chain = e && atoi(e) == 1 && iters >= 2 && cc_smem_bytes(hm) <= 200 * 1024;
+    if (chain) return chained_rounds(in, out, scratch, sc, arms, count, G, H, W, iters, hm, s);
+    return two_pass_rounds(in, out, scratch, sc, arms, count, G, H, W, iters, s);
 }
 
 }  // namespace mccnn
@@ -185,7 +235,7 @@ int mccnn_cbca_to(const float *in, float *out, float *scratch, const uint8_t *ar
         MCCNN_REQUIRE(row_bounds[r] < row_bounds[r + 1] && dst[r], "cbca_to: empty part or null destination %d", r);
         sc.base[r] = reinterpret_cast<float4 *>(dst[r]);
     }
-    return separable_rounds(in, out, scratch, &sc, arms, count, G, H, W, iters, (cudaStream_t)stream);
+    return separable_rounds(in, out, scratch, &sc, arms, count, G, H, W, iters, 13, (cudaStream_t)stream);
 }
 
 int mccnn_cbca(const float *in, float *out, float *scratch, const uint8_t *arms, const int32_t *count, int D, int H,
@@ -204,7 +254,7 @@ int mccnn_cbca(const float *in, float *out, float *scratch, const uint8_t *arms,
         MCCNN_CUDA(cudaMemcpyAsync(out, in, (size_t)H * W * Dp * sizeof(float), cudaMemcpyDeviceToDevice, s));
         return MCCNN_OK;
     }
-    if (mode == MCCNN_CBCA_SEPARABLE) return separable_rounds(in, out, scratch, nullptr, arms, count, G, H, W, iters, s);
+    if (mode == MCCNN_CBCA_SEPARABLE) return separable_rounds(in, out, scratch, nullptr, arms, count, G, H, W, iters, dist - 1, s);
     // exact: ping-pong so that the last round lands in `out`
     float *buf[2];
     buf[(iters - 1) & 1] = out;

@@ -1,0 +1,190 @@
+// Separable cross-based aggregation, fused ACROSS rounds.
+//
+// One round is  out_k(h,w) = ( sum_{h' in spine(h,w)} Hs_k(h',w) ) / |U(h,w)|,  Hs_k(h,w) = sum_{w' in arm(h,w)} out_{k-1}(h,w')
+// (pf:640-650, :157-161).  As two streaming passes (cbca_stream.cuh) a round moves 16 B per cell through HBM: Hs_k out
+// and back, out_k out and back.  k_cbca_colrow runs the column pass of round k and the row pass of round k+1 as ONE
+// kernel with out_k in shared memory only:
+//     Hs_k -> [out_k] -> Hs_{k+1},   8 B per cell per round;   a call of n rounds is  rows | (n-1) x colrow | cols.
+// Fusing this way needs no vertical on-chip state (fusing the two passes of one round needs up to 27 row sums per
+// column on chip).
+//
+// A CTA owns a segment of S pixels of ONE image row x 16 disparity granules (256 threads = 16 pixel slots x 16 lanes).
+//   load    every (pixel, granule) item of the segment and of one halo pixel per side: Hs_k of rows h-1, h, h+1 by
+//           cp.async into shared memory, unconditionally (no dependent step; rows h-1 / h+1 are other CTAs' centre
+//           rows, i.e. L2 hits).  Meanwhile one thread per pixel reads the pixel's arms and |U| and leaves
+//           (arms, |U|, RN(1/|U|)) in shared memory: the per-pixel work is done once, not by each of the 16 lanes.
+//   column  out_k = (Hs_k(h) + up to `up` rows above + up to `down` rows below) / |U| into the tile T; rows beyond
+//           +-1 (4 % of the arms of a natural image) come from global memory, four loads at a time.
+//   row     Hs_{k+1} = sum of out_k along the horizontal arm, from T; stored.
+// The next row pass reaches a data-dependent halo left and right of the segment (at most distance_threshold - 1
+// pixels, usually 0 or 1): one halo pixel per side is always computed; a segment whose arms reach further computes the
+// far halo pixels straight from global memory (one segment in ten).
+// Same additions in the same order as the two-pass form => bit-identical to it (tests: *_match_two_pass).
+#pragma once
+#include "cbca_stream.cuh"
+
+namespace mccnn {
+
+constexpr int CC_S = 62, CC_THREADS = 256, CC_MIN_BLOCKS = 4, CC_SLOTS = CC_THREADS / CS_GC;
+constexpr int CC_NP = CC_S + 2;                              // pixels with staged rows: the segment + one halo pixel per side
+                                                             // (64 = four sweeps of the 16 pixel slots; 56.3 KB at arm limit 13: 4 CTAs per SM)
+
+// dynamic shared memory for a maximum arm length of hm pixels: T | U | Dn | per-pixel info
+static inline size_t cc_smem_bytes(int hm) { return (size_t)((CC_S + 2 * hm) + 2 * CC_NP) * 256 + (size_t)CC_NP * 16; }
+
+__device__ __forceinline__ float4 cc_lds128(unsigned a) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];\n" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ uint4 cc_lds128u(unsigned a) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];\n" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void cc_sts128(unsigned a, const float4 v) {
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};\n" ::"r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ void cc_sts128u(unsigned a, const uint4 v) {
+    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};\n" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ void cc_cp16(unsigned smem, const void *g) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(smem), "l"(g) : "memory");
+}
+
+// the quotient of cs_divide with the reciprocal supplied (y = 1.0f / n, once per pixel)
+__device__ __forceinline__ float4 cc_divide(float4 acc, const float n, const float y) {
+    const float vmax = fmaxf(fmaxf(fabsf(acc.x), fabsf(acc.y)), fmaxf(fabsf(acc.z), fabsf(acc.w)));
+    const float vmin = fminf(fminf(fabsf(acc.x), fabsf(acc.y)), fminf(fabsf(acc.z), fabsf(acc.w)));
+    if (vmax < 1e30f && vmin > 1e-30f)
+        return make_float4(cs_div1(acc.x, n, y), cs_div1(acc.y, n, y), cs_div1(acc.z, n, y), cs_div1(acc.w, n, y));
+    return make_float4(acc.x / n, acc.y / n, acc.z / n, acc.w / n);
+}
+
+// acc + c[k0 * stride] + .. + c[k1 * stride] added in that order, the loads of four steps issued together
+__device__ __noinline__ float4 cc_walk(float4 acc, const float4 *__restrict__ c, const ptrdiff_t stride, int k0, const int k1) {
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (; k0 <= k1; k0 += 4) {
+        const float4 v0 = c[k0 * stride];
+        const float4 v1 = k0 + 1 <= k1 ? c[(k0 + 1) * stride] : z;
+        const float4 v2 = k0 + 2 <= k1 ? c[(k0 + 2) * stride] : z;
+        const float4 v3 = k0 + 3 <= k1 ? c[(k0 + 3) * stride] : z;
+        cs_add(acc, v0);
+        if (k0 + 1 <= k1) cs_add(acc, v1);
+        if (k0 + 2 <= k1) cs_add(acc, v2);
+        if (k0 + 3 <= k1) cs_add(acc, v3);
+    }
+    return acc;
+}
+
+__global__ void __launch_bounds__(CC_THREADS, CC_MIN_BLOCKS) k_cbca_colrow(const float4 *__restrict__ src, float4 *__restrict__ dst,
+                                                                           const uchar4 *__restrict__ arms, const int32_t *__restrict__ count,
+                                                                           int G, int H, int W, int HM) {
+    constexpr int S = CC_S, NP = CC_NP, SLOTS = CC_SLOTS;
+    extern __shared__ __align__(128) unsigned char cc_raw[];
+    __shared__ int reach[2];
+    // staged pixel p = 0 .. NP-1 is image column w0 - 1 + p; tile pixel t = HM - 1 + p (the tile spans w0 - HM .. w0 + S + HM - 1)
+    const unsigned sT = (unsigned)__cvta_generic_to_shared(cc_raw);   // [S + 2*HM][256 B]  Hs_k(h), then out_k
+    const unsigned sU = sT + (S + 2 * HM) * 256;                      // [NP][256 B]        Hs_k(h-1)
+    const unsigned sD = sU + NP * 256;                                // [NP][256 B]        Hs_k(h+1)
+    const unsigned sP = sD + NP * 256;                                // [NP][16 B]         arms | |U| | 1/|U|
+    const int tid = threadIdx.x, gi = tid & 15, slot = tid >> 4;
+    const int g = blockIdx.x * CS_GC + gi, w0 = blockIdx.y * S, h = blockIdx.z;
+    const bool gok = g < G;
+    const int sv = min(S, W - w0);                                    // valid pixels of the segment
+    const int np = min(NP, W - w0 + 1);                               // staged pixels that exist on the right
+    const int p_lo = w0 > 0 ? 0 : 1;                                  // ... and on the left
+    const ptrdiff_t stride = (ptrdiff_t)W * G;
+    const size_t rowp = (size_t)h * W;
+    const float4 *cbase = src + (rowp + w0 - 1) * G + g;              // staged pixel 0, this lane's granule (not dereferenced if outside)
+    const unsigned my = gi * 16;
+    if (tid == 0) { reach[0] = 0; reach[1] = 0; }
+
+    // ---- load: rows h-1, h, h+1 of every staged (pixel, granule) item, unconditionally
+    if (gok) {
+#pragma unroll
+        for (int i = 0; i < (NP + SLOTS - 1) / SLOTS; i++) {
+            const int p = slot + SLOTS * i;
+            if (p >= p_lo && p < np) {
+                const float4 *c = cbase + (ptrdiff_t)p * G;
+                cc_cp16(sT + (HM - 1 + p) * 256 + my, c);
+                if (h >= 1) cc_cp16(sU + p * 256 + my, c - stride);
+                if (h + 1 < H) cc_cp16(sD + p * 256 + my, c + stride);
+            }
+        }
+    }
+    // ---- per-pixel information, one thread per staged pixel; does some row arm of the segment leave the staged halo?
+    int lneed = 0, rneed = 0;
+    if (tid >= p_lo && tid < np) {
+        const size_t q = rowp + w0 - 1 + tid;
+        const uchar4 a = arms[q];
+        const float n = (float)count[q];
+        cc_sts128u(sP + tid * 16, make_uint4((unsigned)a.x | (unsigned)a.y << 8 | (unsigned)a.z << 16 | (unsigned)a.w << 24,
+                                             __float_as_uint(n), __float_as_uint(1.0f / n), 0u));
+        const int px = tid - 1;
+        if (px >= 0 && px < sv) { lneed = (int)a.z - px; rneed = (int)a.w - (sv - 1 - px); }
+    }
+    const bool far = lneed > 1 || rneed > 1;
+    asm volatile("cp.async.wait_all;\n" ::: "memory");
+    const int any_far = __syncthreads_or(far);
+
+    // ---- column phase: out_k of the staged pixels, each thread in the slots it loaded itself
+    if (gok) {
+#pragma unroll 1
+        for (int p = slot; p < np; p += SLOTS) {
+            if (p < p_lo) continue;
+            const uint4 pi = cc_lds128u(sP + p * 16);
+            const int up = pi.x & 0xff, down = (pi.x >> 8) & 0xff;
+            const unsigned t = sT + (HM - 1 + p) * 256 + my;
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            cs_add(acc, cc_lds128(t));                                             // h, h-1, .., h-up, then h+1, .., h+down
+            if (up >= 1) cs_add(acc, cc_lds128(sU + p * 256 + my));
+            if (up >= 2) acc = cc_walk(acc, cbase + (ptrdiff_t)p * G, -stride, 2, up);
+            if (down >= 1) cs_add(acc, cc_lds128(sD + p * 256 + my));
+            if (down >= 2) acc = cc_walk(acc, cbase + (ptrdiff_t)p * G, stride, 2, down);
+            cc_sts128(t, cc_divide(acc, __uint_as_float(pi.y), __uint_as_float(pi.z)));
+        }
+    }
+    if (any_far) {
+        // rare: out_k of the halo pixels beyond the staged one, straight from global memory
+        if (far) { atomicMax(&reach[0], lneed); atomicMax(&reach[1], rneed); }
+        __syncthreads();
+        const int nl = max(reach[0] - 1, 0), nr = max(reach[1] - 1, 0);
+        for (int it = tid; it < (nl + nr) * CS_GC; it += CC_THREADS) {
+            const int q = it >> 4;
+            const int fx = q < nl ? -2 - q : S + 1 + (q - nl);                     // segment-relative column
+            const int x = w0 + fx;
+            if (!gok || x < 0 || x >= W) continue;
+            const uchar4 a = arms[rowp + x];
+            const float n = (float)count[rowp + x];
+            const float4 *c = src + (rowp + x) * G + g;
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            cs_add(acc, c[0]);
+            acc = cc_walk(acc, c, -stride, 1, a.x);
+            acc = cc_walk(acc, c, stride, 1, a.y);
+            cc_sts128(sT + (HM + fx) * 256 + my, cc_divide(acc, n, 1.0f / n));
+        }
+    }
+    __syncthreads();
+
+    // ---- row phase: Hs_{k+1} of the segment from shared memory
+    if (gok) {
+        float4 *out = dst + (rowp + w0) * G + g;
+#pragma unroll 1
+        for (int px = slot; px < sv; px += SLOTS) {
+            unsigned a;
+            asm volatile("ld.shared.u32 %0, [%1];\n" : "=r"(a) : "r"(sP + (px + 1) * 16));
+            const unsigned t0 = sT + (HM + px) * 256 + my;
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            cs_add(acc, cc_lds128(t0));                                            // w, w-1, .., w-left, then w+1, .., w+right
+            const unsigned tl = t0 - ((a >> 16) & 0xff) * 256, tr = t0 + (a >> 24) * 256;
+#pragma unroll 1
+            for (unsigned t = t0; t != tl;) { t -= 256; cs_add(acc, cc_lds128(t)); }
+#pragma unroll 1
+            for (unsigned t = t0; t != tr;) { t += 256; cs_add(acc, cc_lds128(t)); }
+            out[(size_t)px * G] = acc;
+        }
+    }
+}
+
+}  // namespace mccnn
