@@ -512,15 +512,16 @@ def run_ours(args):
         it1, it2 = int(hp["cbca_num_iterations1"]), int(hp["cbca_num_iterations2"])
         cells_rank = cells / world if slab else cells           # a rank's slab of every volume
         # algorithmic bytes per stage and launches of the stage's main kernel
-        # ("launch" of a CBCA round = its two streaming passes (k_cbca_pass, rows then columns) on one volume; the
-        #  algorithmic figure is the fused minimum of 8 B/cell/round, the two passes actually move 16 B/cell)
+        # ("launch" of a CBCA round = one round on one volume: a call of n rounds is  k_cbca_pass<rows> | (n-1) x
+        #  k_cbca_colrow | k_cbca_pass<cols>, n + 1 kernels that each move 8 B/cell; the algorithmic figure is 8 B/cell/round)
+        cbca_kernels = "k_cbca_colrow (+ k_cbca_pass<rows> / <cols> at the ends of a call)"
         model = {
-            "cbca2": (8.0 * cells_rank * it2 * 2, it2 * 2, "k_cbca_pass<rows>+k_cbca_pass<cols>"),
+            "cbca2": (8.0 * cells_rank * it2 * 2, it2 * 2, cbca_kernels),
         } if slab else {
             "cost_volume": ((8.0 + 512.0 / D) * cells, 1, "k_cost_volume_tc (+k_cost_fill)"),
-            "cbca1": (8.0 * cells * it1 * 2, it1 * 2, "k_cbca_pass<rows>+k_cbca_pass<cols>"),
+            "cbca1": (8.0 * cells * it1 * 2, it1 * 2, cbca_kernels),
             "sgm": (8.0 * cells * 4 * 2, 4, "k_sgm_pass"),
-            "cbca2": (8.0 * cells * it2 * 2, it2 * 2, "k_cbca_pass<rows>+k_cbca_pass<cols>"),
+            "cbca2": (8.0 * cells * it2 * 2, it2 * 2, cbca_kernels),
             "wta": (4.0 * cells * 2, 2, "k_wta"),
         }
         kernels = {}
@@ -547,8 +548,7 @@ def run_ours(args):
                     "traffic_source": (traffic.get(dom) or {}).get("source"), "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": nbytes / nl, "avg_launch_ms": acc[dom] / nl}
         if roofline["traffic"]:
-            # what the kernel(s) of one launch actually move (ncu) against the same peak: the default CBCA round is
-            # two passes, i.e. twice the algorithmic bytes, and runs close to copy speed on those
+            # what the kernels of one round actually move (ncu) against the same peak
             roofline["traffic_frac"] = roofline["traffic"] / (roofline["avg_launch_ms"] * 1e-3) / 1e9 / peak
         cfg = bench_config(args.workload, args.image)
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,

@@ -81,12 +81,17 @@ int mccnn_cross_region_list(const uint8_t *arms, int32_t *region, int H, int W,
  * more HWD volume.
  * mode MCCNN_CBCA_SEPARABLE (default): row sums re-used down each column (<= 54 additions per cell at
  *      distance_threshold 14); equals the reference up to float32 re-association of the sum (~1e-7 relative).
- *      Two streaming passes per round (rows into `scratch`, columns into `out`): `scratch` is needed for any
- *      iters >= 1.
+ *      The rounds of a call are chained: one row pass, then per further round ONE kernel (k_cbca_colrow) that forms a
+ *      round's column sums + division in shared memory and the next round's row sums from them, then one column pass:
+ *      8 instead of 16 B per cell per round through HBM.  `scratch` is needed for any iters >= 1.
+ * mode MCCNN_CBCA_SEPARABLE_TWO_PASS: the same sums in the same order as two streaming passes per round (rows into
+ *      `scratch`, columns into `out`).  Bit-identical to MCCNN_CBCA_SEPARABLE; faster than it on piece-wise constant
+ *      images whose vertical arms all sit at the distance limit, slower on natural ones; also the cross-check of the
+ *      chained kernel.
  * mode MCCNN_CBCA_EXACT: one float32 running sum over the whole region in the reference's enumeration
  *      order (pf:149-163), bit-identical to the reference (<= 729 additions per cell); `scratch` for iters >= 2.
- * distance_threshold (1..255) is the value the arms were built with. */
-enum mccnn_cbca_mode { MCCNN_CBCA_SEPARABLE = 0, MCCNN_CBCA_EXACT = 1 };
+ * distance_threshold (1..255) must be the value the arms were built with (it sizes the chained kernel's tile). */
+enum mccnn_cbca_mode { MCCNN_CBCA_SEPARABLE = 0, MCCNN_CBCA_EXACT = 1, MCCNN_CBCA_SEPARABLE_TWO_PASS = 2 };
 int mccnn_cbca(const float *in, float *out, float *scratch, const uint8_t *arms,
                const int32_t *count, int D, int H, int W, int iters, int distance_threshold, int mode,
                void *stream);
@@ -145,7 +150,7 @@ int mccnn_cost_volume_slab(const float *fl, const float *fr, float *L, float *R,
  * row_bounds[r+1] -- a row slab [rows_r][W][4 * g_total] of the owner (peer memory), at granule offset g_offset.
  * `out` holds the intermediate rounds.  row_bounds (nparts + 1) and dst (nparts device pointers) are HOST arrays. */
 int mccnn_cbca_to(const float *in, float *out, float *scratch, const uint8_t *arms, const int32_t *count,
-                  int D, int H, int W, int iters, int nparts, const int *row_bounds,
+                  int D, int H, int W, int iters, int distance_threshold, int nparts, const int *row_bounds,
                   float *const *dst, int g_offset, int g_total, void *stream);
 
 /* a6/a7: two of the four chained passes (pf:194-208).  which = 0: (0,1) then (0,-1) on a ROW slab -- volumes

@@ -38,7 +38,7 @@ SIGNATURES = {
     "mccnn_bilateral": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _vp]),
     "mccnn_cost_volume_slab": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "mccnn_sgm_passes_slab": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _d, _d, _d, _d, _d, _d, _vp]),
-    "mccnn_cbca_to": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _i, _i, _vp]),
+    "mccnn_cbca_to": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _i, _i, _vp]),
     "mccnn_sgm_passes_slab_to": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _d, _d, _d, _d, _d, _d, _i, _vp, _vp, _vp,
                                       _i, _vp]),
     "mccnn_wta_slab": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp]),

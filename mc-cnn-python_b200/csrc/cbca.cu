@@ -10,7 +10,6 @@
 #include "common.cuh"
 #include "cbca_stream.cuh"
 #include "cbca_chain.cuh"
-#include <stdlib.h>
 
 namespace mccnn {
 
@@ -179,12 +178,10 @@ static int chained_rounds(const float *in, float *out, float *scratch, const CsS
     return MCCNN_OK;
 }
 
-// MCCNN_CBCA_CHAIN=1 (tuning / cross-check) selects the chained rounds; the default is two streaming passes per round
+// the default: chained rounds wherever they apply (two rounds or more; the shared-memory tile grows with the arm limit)
 static int separable_rounds(const float *in, float *out, float *scratch, const CsScatter *sc, const uint8_t *arms,
                             const int32_t *count, int G, int H, int W, int iters, int hm, cudaStream_t s) {
-    const char *e = getenv("MCCNN_CBCA_CHAIN");
-    const bool chain = e && atoi(e) == 1 && iters >= 2 && cc_smem_bytes(hm) <= 200 * 1024;
-    if (chain) return chained_rounds(in, out, scratch, sc, arms, count, G, H, W, iters, hm, s);
+    if (iters >= 2 && cc_smem_bytes(hm) <= 200 * 1024) return chained_rounds(in, out, scratch, sc, arms, count, G, H, W, iters, hm, s);
     return two_pass_rounds(in, out, scratch, sc, arms, count, G, H, W, iters, s);
 }
 
@@ -218,10 +215,11 @@ int mccnn_cross_region_list(const uint8_t *arms, int32_t *region, int H, int W, 
 }
 
 int mccnn_cbca_to(const float *in, float *out, float *scratch, const uint8_t *arms, const int32_t *count, int D, int H,
-                  int W, int iters, int nparts, const int *row_bounds, float *const *dst, int g_offset, int g_total,
+                  int W, int iters, int dist, int nparts, const int *row_bounds, float *const *dst, int g_offset, int g_total,
                   void *stream) {
     MCCNN_REQUIRE(in && out && scratch && arms && count && D >= 1 && H >= 1 && W >= 1 && iters >= 1, "cbca_to: bad arguments");
     MCCNN_REQUIRE(H <= 65535 && W <= 65535, "cbca_to: image too large");
+    MCCNN_REQUIRE(dist >= 1 && dist <= 255, "cbca_to: distance_threshold %d outside [1, 255]", dist);
     MCCNN_REQUIRE(in != out && scratch != in && scratch != out, "cbca_to: in, out and scratch must differ");
     MCCNN_REQUIRE(nparts >= 1 && nparts <= CS_MAX_PARTS && row_bounds && dst, "cbca_to: 1 to %d parts", CS_MAX_PARTS);
     MCCNN_REQUIRE(row_bounds[0] == 0 && row_bounds[nparts] == H, "cbca_to: row bounds must tile [0, %d)", H);
@@ -235,12 +233,13 @@ int mccnn_cbca_to(const float *in, float *out, float *scratch, const uint8_t *ar
         MCCNN_REQUIRE(row_bounds[r] < row_bounds[r + 1] && dst[r], "cbca_to: empty part or null destination %d", r);
         sc.base[r] = reinterpret_cast<float4 *>(dst[r]);
     }
-    return separable_rounds(in, out, scratch, &sc, arms, count, G, H, W, iters, 13, (cudaStream_t)stream);
+    return separable_rounds(in, out, scratch, &sc, arms, count, G, H, W, iters, dist - 1, (cudaStream_t)stream);
 }
 
 int mccnn_cbca(const float *in, float *out, float *scratch, const uint8_t *arms, const int32_t *count, int D, int H,
                int W, int iters, int dist, int mode, void *stream) {
-    MCCNN_REQUIRE(mode == MCCNN_CBCA_SEPARABLE || mode == MCCNN_CBCA_EXACT, "cbca: unknown mode %d", mode);
+    MCCNN_REQUIRE(mode == MCCNN_CBCA_SEPARABLE || mode == MCCNN_CBCA_EXACT || mode == MCCNN_CBCA_SEPARABLE_TWO_PASS,
+                  "cbca: unknown mode %d", mode);
     MCCNN_REQUIRE(dist >= 1 && dist <= 255, "cbca: distance_threshold %d outside [1, 255]", dist);
     MCCNN_REQUIRE(in && out && arms && count && D >= 1 && H >= 1 && W >= 1 && iters >= 0, "cbca: bad arguments");
     MCCNN_REQUIRE(H <= 65535 && W <= 65535, "cbca: image too large");
@@ -255,6 +254,7 @@ int mccnn_cbca(const float *in, float *out, float *scratch, const uint8_t *arms,
         return MCCNN_OK;
     }
     if (mode == MCCNN_CBCA_SEPARABLE) return separable_rounds(in, out, scratch, nullptr, arms, count, G, H, W, iters, dist - 1, s);
+    if (mode == MCCNN_CBCA_SEPARABLE_TWO_PASS) return two_pass_rounds(in, out, scratch, nullptr, arms, count, G, H, W, iters, s);
     // exact: ping-pong so that the last round lands in `out`
     float *buf[2];
     buf[(iters - 1) & 1] = out;

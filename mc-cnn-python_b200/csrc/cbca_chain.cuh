@@ -100,16 +100,20 @@ __global__ void __launch_bounds__(CC_THREADS, CC_MIN_BLOCKS) k_cbca_colrow(const
     const unsigned my = gi * 16;
     if (tid == 0) { reach[0] = 0; reach[1] = 0; }
 
-    // ---- load: rows h-1, h, h+1 of every staged (pixel, granule) item, unconditionally
+    // ---- load: rows h-1, h, h+1 of every staged (pixel, granule) item, unconditionally (running pointers: the 64-bit
+    //      address arithmetic is done once per thread, not once per item)
     if (gok) {
+        const char *c = reinterpret_cast<const char *>(cbase + (ptrdiff_t)slot * G);
+        const ptrdiff_t strideB = stride * 16, stepB = (ptrdiff_t)SLOTS * G * 16;
+        const bool has_up = h >= 1, has_dn = h + 1 < H;
+        unsigned t = sT + (HM - 1 + slot) * 256 + my, u = sU + slot * 256 + my;
 #pragma unroll
-        for (int i = 0; i < (NP + SLOTS - 1) / SLOTS; i++) {
+        for (int i = 0; i < (NP + SLOTS - 1) / SLOTS; i++, c += stepB, t += SLOTS * 256, u += SLOTS * 256) {
             const int p = slot + SLOTS * i;
             if (p >= p_lo && p < np) {
-                const float4 *c = cbase + (ptrdiff_t)p * G;
-                cc_cp16(sT + (HM - 1 + p) * 256 + my, c);
-                if (h >= 1) cc_cp16(sU + p * 256 + my, c - stride);
-                if (h + 1 < H) cc_cp16(sD + p * 256 + my, c + stride);
+                cc_cp16(t, c);
+                if (has_up) cc_cp16(u, c - strideB);
+                if (has_dn) cc_cp16(u + NP * 256, c + strideB);
             }
         }
     }
@@ -125,22 +129,24 @@ __global__ void __launch_bounds__(CC_THREADS, CC_MIN_BLOCKS) k_cbca_colrow(const
         if (px >= 0 && px < sv) { lneed = (int)a.z - px; rneed = (int)a.w - (sv - 1 - px); }
     }
     const bool far = lneed > 1 || rneed > 1;
-    asm volatile("cp.async.wait_all;\n" ::: "memory");
+    // (the barrier only publishes the per-pixel information: it comes BEFORE the wait for the staged rows, so that a warp
+    //  whose own rows have arrived does not wait for the slowest warp's)
     const int any_far = __syncthreads_or(far);
+    asm volatile("cp.async.wait_all;\n" ::: "memory");
 
     // ---- column phase: out_k of the staged pixels, each thread in the slots it loaded itself
     if (gok) {
+        unsigned t = sT + (HM - 1 + slot) * 256 + my, u = sU + slot * 256 + my, pa = sP + slot * 16;
 #pragma unroll 1
-        for (int p = slot; p < np; p += SLOTS) {
+        for (int p = slot; p < np; p += SLOTS, t += SLOTS * 256, u += SLOTS * 256, pa += SLOTS * 16) {
             if (p < p_lo) continue;
-            const uint4 pi = cc_lds128u(sP + p * 16);
+            const uint4 pi = cc_lds128u(pa);
             const int up = pi.x & 0xff, down = (pi.x >> 8) & 0xff;
-            const unsigned t = sT + (HM - 1 + p) * 256 + my;
             float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
             cs_add(acc, cc_lds128(t));                                             // h, h-1, .., h-up, then h+1, .., h+down
-            if (up >= 1) cs_add(acc, cc_lds128(sU + p * 256 + my));
+            if (up >= 1) cs_add(acc, cc_lds128(u));
             if (up >= 2) acc = cc_walk(acc, cbase + (ptrdiff_t)p * G, -stride, 2, up);
-            if (down >= 1) cs_add(acc, cc_lds128(sD + p * 256 + my));
+            if (down >= 1) cs_add(acc, cc_lds128(u + NP * 256));
             if (down >= 2) acc = cc_walk(acc, cbase + (ptrdiff_t)p * G, stride, 2, down);
             cc_sts128(t, cc_divide(acc, __uint_as_float(pi.y), __uint_as_float(pi.z)));
         }
@@ -169,12 +175,13 @@ __global__ void __launch_bounds__(CC_THREADS, CC_MIN_BLOCKS) k_cbca_colrow(const
 
     // ---- row phase: Hs_{k+1} of the segment from shared memory
     if (gok) {
-        float4 *out = dst + (rowp + w0) * G + g;
+        char *out = reinterpret_cast<char *>(dst + (rowp + w0 + slot) * G + g);
+        const ptrdiff_t stepB = (ptrdiff_t)SLOTS * G * 16;
+        unsigned t0 = sT + (HM + slot) * 256 + my, pa = sP + (slot + 1) * 16;
 #pragma unroll 1
-        for (int px = slot; px < sv; px += SLOTS) {
+        for (int px = slot; px < sv; px += SLOTS, t0 += SLOTS * 256, pa += SLOTS * 16, out += stepB) {
             unsigned a;
-            asm volatile("ld.shared.u32 %0, [%1];\n" : "=r"(a) : "r"(sP + (px + 1) * 16));
-            const unsigned t0 = sT + (HM + px) * 256 + my;
+            asm volatile("ld.shared.u32 %0, [%1];\n" : "=r"(a) : "r"(pa));
             float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
             cs_add(acc, cc_lds128(t0));                                            // w, w-1, .., w-left, then w+1, .., w+right
             const unsigned tl = t0 - ((a >> 16) & 0xff) * 256, tr = t0 + (a >> 24) * 256;
@@ -182,7 +189,7 @@ __global__ void __launch_bounds__(CC_THREADS, CC_MIN_BLOCKS) k_cbca_colrow(const
             for (unsigned t = t0; t != tl;) { t -= 256; cs_add(acc, cc_lds128(t)); }
 #pragma unroll 1
             for (unsigned t = t0; t != tr;) { t += 256; cs_add(acc, cc_lds128(t)); }
-            out[(size_t)px * G] = acc;
+            *reinterpret_cast<float4 *>(out) = acc;
         }
     }
 }

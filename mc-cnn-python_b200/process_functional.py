@@ -28,10 +28,13 @@ __all__ = ["compute_features", "compute_cost_volume", "cost_volume_aggregation",
 
 # Summation order of cross-based aggregation (mccnn_cbca `mode`):
 #   0 = "separable" (default): row sums re-used down each column, <= 54 additions per cell; differs
-#       from the reference only by float32 re-association (~1e-7 relative);
+#       from the reference only by float32 re-association (~1e-7 relative); the rounds of a call are
+#       chained (column pass of round k + row pass of round k+1 in one kernel, 8 B/cell/round);
 #   1 = "exact": the reference's flat running sum over the whole region (pf:157-161), bit-identical
-#       to the reference, <= 729 additions per cell.
-CBCA_SEPARABLE, CBCA_EXACT = 0, 1
+#       to the reference, <= 729 additions per cell;
+#   2 = "separable, two passes per round": the sums of mode 0, identical bits, 16 B/cell/round -- the
+#       better choice for piece-wise constant images (every vertical arm at the limit), and the cross-check.
+CBCA_SEPARABLE, CBCA_EXACT, CBCA_SEPARABLE_TWO_PASS = 0, 1, 2
 CBCA_MODE = CBCA_SEPARABLE
 
 

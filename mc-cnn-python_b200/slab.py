@@ -319,7 +319,7 @@ class SlabRank(object):
         for v in range(2):
             dst = (ctypes.c_void_p * n)(*[bases[j] + 4 * (2 + v) * self.region for j in range(n)])
             call("mccnn_cbca_to", p(self.volA[v]), p(self.volB[v]), p(self.volS), p(self.arms[v]), p(self.count[v]), self.Dl,
-                 H, W, it1, n, bounds, dst, pl.granules[self.rank][0], pl.G, sp())
+                 H, W, it1, int(hp["cbca_distance"]), n, bounds, dst, pl.granules[self.rank][0], pl.G, sp())
 
     def _cbca(self, i, src, dst, iters):
         p, call, sp, hp, pl = _ffi.ptr, _ffi.call, _ffi.stream_ptr, self.hp, self.plan

@@ -24,6 +24,8 @@ for image, maker in (("natural", synth_pair), ("flat", flat_pair)):
         a.record(); run(rounds); b.record(); torch.cuda.synchronize()
         ms = a.elapsed_time(b) / rounds
         print("  %-52s %.3f ms per round (call of %d)  %.0f GB/s (8 B/cell)" % (name, ms, rounds, 8.0 * H * W * D / ms / 1e6), flush=True)
-    bench(0, "separable, two streaming passes per round (default)")
+    bench(0, "separable, chained rounds (default)")
+    bench(0, "separable, chained rounds, call of 2", rounds=2)
+    bench(2, "separable, two streaming passes per round")
     if "--exact" in sys.argv:
         bench(1, "exact (flat walk, bit-identical to reference)", rounds=2)

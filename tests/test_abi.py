@@ -127,10 +127,10 @@ def test_slab_entry_points_validate_before_touching_the_device(pkg):
                                       0, None)
     assert rc == -1 and b"parts" in err()
     rows = (ctypes.c_int * 3)(0, 2, 5)
-    rc = lib.mccnn_cbca_to(one, ctypes.c_void_p(32), ctypes.c_void_p(48), one, one, 8, 4, 20, 2, 2, rows, dst, 0, 2, None)
+    rc = lib.mccnn_cbca_to(one, ctypes.c_void_p(32), ctypes.c_void_p(48), one, one, 8, 4, 20, 2, 14, 2, rows, dst, 0, 2, None)
     assert rc == -1 and b"tile" in err()
     rows = (ctypes.c_int * 3)(0, 2, 4)
-    rc = lib.mccnn_cbca_to(one, ctypes.c_void_p(32), ctypes.c_void_p(48), one, one, 8, 4, 20, 2, 2, rows, dst, 1, 2, None)
+    rc = lib.mccnn_cbca_to(one, ctypes.c_void_p(32), ctypes.c_void_p(48), one, one, 8, 4, 20, 2, 14, 2, rows, dst, 1, 2, None)
     assert rc == -1 and b"pitch" in err()
     assert lib.mccnn_wta_combine(one, one, one, 2, 3, 2, 2, None) == -1                 # slab stride smaller than a map
     assert lib.mccnn_copy3d(ctypes.c_void_p(8), one, 1, 1, 1, 0, 0, 0, 0, None) == -1 and b"aligned" in err()

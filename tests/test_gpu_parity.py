@@ -267,6 +267,30 @@ def test_cbca_separable_many_shapes_vs_oracle(pf, oracle):
         np.testing.assert_allclose(Rt, Ro, atol=CBCA_SEP_RTOL * scale, rtol=0)
 
 
+def test_cbca_chained_rounds_match_two_pass(pf, monkeypatch):
+    """The default mode chains the rounds of a call (rows | column pass of round k + row pass of round k+1 in one
+    kernel, out_k in shared memory only | cols).  It forms the same sums in the same order as two streaming passes per
+    round: IDENTICAL bits.  Covers flat images (13-pixel arms: the far-halo path of every segment and the global walks),
+    widths around the 62-pixel segment (ragged last segment, arms crossing segment borders, a staged halo pixel that
+    does not exist), granule counts that are not a multiple of 16, images shorter than an arm, two to five rounds,
+    distance thresholds other than match.py's 14."""
+    cases = [(40, 90, 70, 4, 3, 14), (33, 47, 192, 30, 2, 14), (9, 29, 33, 1, 2, 14), (50, 21, 40, 2, 3, 14),
+             (64, 64, 32, 1, 2, 14), (17, 200, 29, 3, 2, 14), (70, 40, 100, 2, 2, 14), (12, 129, 8, 1, 4, 14),
+             (25, 300, 20, 1, 5, 14), (31, 191, 68, 2, 3, 20), (14, 140, 12, 1, 2, 40), (20, 65, 6, 1, 3, 3),
+             (5, 64, 4, 2, 2, 1), (3, 128, 130, 1, 2, 14), (30, 62, 16, 1, 3, 14), (30, 63, 16, 1, 3, 14),
+             (30, 125, 16, 2, 3, 14), (300, 700, 48, 6, 4, 14)]
+    for (H, W, D, levels, iters, dist) in cases:
+        li, ri = synth_images(H * W + D, H, W, levels, 2)
+        rng = np.random.default_rng(D)
+        Lv = rng.standard_normal((D, H, W)).astype(np.float32) * 50
+        Rv = rng.standard_normal((D, H, W)).astype(np.float32) * 50
+        monkeypatch.setattr(pf, "CBCA_MODE", pf.CBCA_SEPARABLE_TWO_PASS)
+        Ls, Rs = pf.cost_volume_aggregation(li, ri, Lv, Rv, 0.02, dist, iters)
+        monkeypatch.setattr(pf, "CBCA_MODE", pf.CBCA_SEPARABLE)
+        Lt, Rt = pf.cost_volume_aggregation(li, ri, Lv, Rv, 0.02, dist, iters)
+        assert eq(Ls, Lt) and eq(Rs, Rt), (H, W, D, levels, iters, dist)
+
+
 def test_cbca_every_mode_with_long_arms(pf, oracle, monkeypatch):
     """distance_threshold 20 (arms up to 19 pixels, longer than match.py's 13) on a flat image, every mode, integer
     costs: exact sums, so every mode must equal the oracle bit for bit after one round."""
@@ -274,7 +298,7 @@ def test_cbca_every_mode_with_long_arms(pf, oracle, monkeypatch):
     Li = rng.integers(0, 64, (12, 30, 90)).astype(np.float32)
     li, ri = synth_images(5, 30, 90, 1, 1)
     Lo, _ = oracle.cost_volume_aggregation(li, ri, Li, Li, 0.02, 20, 1)
-    for mode in (pf.CBCA_SEPARABLE, pf.CBCA_EXACT):
+    for mode in (pf.CBCA_SEPARABLE, pf.CBCA_EXACT, pf.CBCA_SEPARABLE_TWO_PASS):
         monkeypatch.setattr(pf, "CBCA_MODE", mode)
         Lg, _ = pf.cost_volume_aggregation(li, ri, Li, Li, 0.02, 20, 1)
         assert eq(Lg, Lo), mode
