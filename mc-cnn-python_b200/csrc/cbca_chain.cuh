@@ -8,7 +8,7 @@
 // Fusing this way needs no vertical on-chip state (fusing the two passes of one round needs up to 27 row sums per
 // column on chip).
 //
-// A CTA owns a segment of S pixels of ONE image row x 16 disparity granules (256 threads = 16 pixel slots x 16 lanes).
+// A CTA owns a segment of S pixels of ONE image row x 16 disparity granules (NT threads = NT / 16 pixel slots x 16 lanes).
 //   load    every (pixel, granule) item of the segment and of one halo pixel per side: Hs_k of rows h-1, h, h+1 by
 //           cp.async into shared memory, unconditionally (no dependent step; rows h-1 / h+1 are other CTAs' centre
 //           rows, i.e. L2 hits).  Meanwhile one thread per pixel reads the pixel's arms and |U| and leaves
@@ -25,12 +25,17 @@
 
 namespace mccnn {
 
-constexpr int CC_S = 62, CC_THREADS = 256, CC_MIN_BLOCKS = 4, CC_SLOTS = CC_THREADS / CS_GC;
-constexpr int CC_NP = CC_S + 2;                              // pixels with staged rows: the segment + one halo pixel per side
-                                                             // (64 = four sweeps of the 16 pixel slots; 56.3 KB at arm limit 13: 4 CTAs per SM)
-
-// dynamic shared memory for a maximum arm length of hm pixels: T | U | Dn | per-pixel info
-static inline size_t cc_smem_bytes(int hm) { return (size_t)((CC_S + 2 * hm) + 2 * CC_NP) * 256 + (size_t)CC_NP * 16; }
+// NP = S + 2 * HL staged pixels (the segment + HL halo pixels per side) = four sweeps of the NT / 16 pixel slots
+template <int S_, int NT_, int MINB_, int HL_>
+struct CcShape {
+    static constexpr int S = S_, NT = NT_, MINB = MINB_, HL = HL_, SLOTS = NT / CS_GC, NP = S + 2 * HL;
+    // dynamic shared memory: Hs_k(h-1) | Hs_k(h) -> out_k | Hs_k(h+1) | per-pixel info.  The far halo of out_k (rare, up to
+    // arm limit - 1 pixels per side) is written over the neighbouring ends of the h-1 / h+1 buffers, which are dead by then.
+    static constexpr size_t SMEM = (size_t)3 * NP * 256 + (size_t)NP * 16;
+    static bool supports(int hm) { return hm - HL <= NP; }
+};
+typedef CcShape<30, 128, 8, 1> CcNarrow;     // 25 KB, 8 CTAs of 4 warps per SM (the one used: shorter waits at the two barriers)
+typedef CcShape<62, 256, 4, 1> CcWide;       // 50 KB, 4 CTAs of 8 warps per SM
 
 __device__ __forceinline__ float4 cc_lds128(unsigned a) {
     float4 v;
@@ -77,26 +82,41 @@ __device__ __noinline__ float4 cc_walk(float4 acc, const float4 *__restrict__ c,
     return acc;
 }
 
-__global__ void __launch_bounds__(CC_THREADS, CC_MIN_BLOCKS) k_cbca_colrow(const float4 *__restrict__ src, float4 *__restrict__ dst,
-                                                                           const uchar4 *__restrict__ arms, const int32_t *__restrict__ count,
-                                                                           int G, int H, int W, int HM) {
-    constexpr int S = CC_S, NP = CC_NP, SLOTS = CC_SLOTS;
+// rows 2 .. n of an arm (n >= 2): rows 2 and 3 inline with both loads in flight (most long arms end there), the rest by cc_walk
+__device__ __forceinline__ float4 cc_far_rows(float4 acc, const float4 *__restrict__ c, const ptrdiff_t stride, const int n) {
+    const float4 v2 = c[2 * stride];
+    if (n >= 3) {
+        const float4 v3 = c[3 * stride];
+        cs_add(acc, v2);
+        cs_add(acc, v3);
+        if (n >= 4) acc = cc_walk(acc, c, stride, 4, n);
+    } else {
+        cs_add(acc, v2);
+    }
+    return acc;
+}
+
+template <class C>
+__global__ void __launch_bounds__(C::NT, C::MINB) k_cbca_colrow(const float4 *__restrict__ src, float4 *__restrict__ dst,
+                                                                const uchar4 *__restrict__ arms, const int32_t *__restrict__ count,
+                                                                int G, int H, int W) {
+    constexpr int S = C::S, NP = C::NP, SLOTS = C::SLOTS, HL = C::HL;
     extern __shared__ __align__(128) unsigned char cc_raw[];
     __shared__ int reach[2];
-    // staged pixel p = 0 .. NP-1 is image column w0 - 1 + p; tile pixel t = HM - 1 + p (the tile spans w0 - HM .. w0 + S + HM - 1)
-    const unsigned sT = (unsigned)__cvta_generic_to_shared(cc_raw);   // [S + 2*HM][256 B]  Hs_k(h), then out_k
-    const unsigned sU = sT + (S + 2 * HM) * 256;                      // [NP][256 B]        Hs_k(h-1)
-    const unsigned sD = sU + NP * 256;                                // [NP][256 B]        Hs_k(h+1)
-    const unsigned sP = sD + NP * 256;                                // [NP][16 B]         arms | |U| | 1/|U|
+    // staged pixel p = 0 .. NP-1 is image column w0 - HL + p
+    const unsigned sU = (unsigned)__cvta_generic_to_shared(cc_raw);   // [NP][256 B]  Hs_k(h-1)
+    const unsigned sT = sU + NP * 256;                                // [NP][256 B]  Hs_k(h), then out_k
+    const unsigned sD = sT + NP * 256;                                // [NP][256 B]  Hs_k(h+1)
+    const unsigned sP = sD + NP * 256;                                // [NP][16 B]   arms | |U| | 1/|U|
     const int tid = threadIdx.x, gi = tid & 15, slot = tid >> 4;
     const int g = blockIdx.x * CS_GC + gi, w0 = blockIdx.y * S, h = blockIdx.z;
     const bool gok = g < G;
     const int sv = min(S, W - w0);                                    // valid pixels of the segment
-    const int np = min(NP, W - w0 + 1);                               // staged pixels that exist on the right
-    const int p_lo = w0 > 0 ? 0 : 1;                                  // ... and on the left
+    const int np = min(NP, W - w0 + HL);                              // staged pixels that exist on the right
+    const int p_lo = w0 > 0 ? 0 : HL;                                 // ... and on the left
     const ptrdiff_t stride = (ptrdiff_t)W * G;
     const size_t rowp = (size_t)h * W;
-    const float4 *cbase = src + (rowp + w0 - 1) * G + g;              // staged pixel 0, this lane's granule (not dereferenced if outside)
+    const float4 *cbase = src + (rowp + w0 - HL) * G + g;              // staged pixel 0, this lane's granule (not dereferenced if outside)
     const unsigned my = gi * 16;
     if (tid == 0) { reach[0] = 0; reach[1] = 0; }
 
@@ -106,29 +126,29 @@ __global__ void __launch_bounds__(CC_THREADS, CC_MIN_BLOCKS) k_cbca_colrow(const
         const char *c = reinterpret_cast<const char *>(cbase + (ptrdiff_t)slot * G);
         const ptrdiff_t strideB = stride * 16, stepB = (ptrdiff_t)SLOTS * G * 16;
         const bool has_up = h >= 1, has_dn = h + 1 < H;
-        unsigned t = sT + (HM - 1 + slot) * 256 + my, u = sU + slot * 256 + my;
+        unsigned t = sT + slot * 256 + my;
 #pragma unroll
-        for (int i = 0; i < (NP + SLOTS - 1) / SLOTS; i++, c += stepB, t += SLOTS * 256, u += SLOTS * 256) {
+        for (int i = 0; i < (NP + SLOTS - 1) / SLOTS; i++, c += stepB, t += SLOTS * 256) {
             const int p = slot + SLOTS * i;
             if (p >= p_lo && p < np) {
                 cc_cp16(t, c);
-                if (has_up) cc_cp16(u, c - strideB);
-                if (has_dn) cc_cp16(u + NP * 256, c + strideB);
+                if (has_up) cc_cp16(t - NP * 256, c - strideB);
+                if (has_dn) cc_cp16(t + NP * 256, c + strideB);
             }
         }
     }
     // ---- per-pixel information, one thread per staged pixel; does some row arm of the segment leave the staged halo?
     int lneed = 0, rneed = 0;
     if (tid >= p_lo && tid < np) {
-        const size_t q = rowp + w0 - 1 + tid;
+        const size_t q = rowp + w0 - HL + tid;
         const uchar4 a = arms[q];
         const float n = (float)count[q];
         cc_sts128u(sP + tid * 16, make_uint4((unsigned)a.x | (unsigned)a.y << 8 | (unsigned)a.z << 16 | (unsigned)a.w << 24,
                                              __float_as_uint(n), __float_as_uint(1.0f / n), 0u));
-        const int px = tid - 1;
+        const int px = tid - HL;
         if (px >= 0 && px < sv) { lneed = (int)a.z - px; rneed = (int)a.w - (sv - 1 - px); }
     }
-    const bool far = lneed > 1 || rneed > 1;
+    const bool far = lneed > HL || rneed > HL;
     // (the barrier only publishes the per-pixel information: it comes BEFORE the wait for the staged rows, so that a warp
     //  whose own rows have arrived does not wait for the slowest warp's)
     const int any_far = __syncthreads_or(far);
@@ -136,29 +156,30 @@ __global__ void __launch_bounds__(CC_THREADS, CC_MIN_BLOCKS) k_cbca_colrow(const
 
     // ---- column phase: out_k of the staged pixels, each thread in the slots it loaded itself
     if (gok) {
-        unsigned t = sT + (HM - 1 + slot) * 256 + my, u = sU + slot * 256 + my, pa = sP + slot * 16;
+        unsigned t = sT + slot * 256 + my, pa = sP + slot * 16;
 #pragma unroll 1
-        for (int p = slot; p < np; p += SLOTS, t += SLOTS * 256, u += SLOTS * 256, pa += SLOTS * 16) {
+        for (int p = slot; p < np; p += SLOTS, t += SLOTS * 256, pa += SLOTS * 16) {
             if (p < p_lo) continue;
             const uint4 pi = cc_lds128u(pa);
             const int up = pi.x & 0xff, down = (pi.x >> 8) & 0xff;
             float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
             cs_add(acc, cc_lds128(t));                                             // h, h-1, .., h-up, then h+1, .., h+down
-            if (up >= 1) cs_add(acc, cc_lds128(u));
-            if (up >= 2) acc = cc_walk(acc, cbase + (ptrdiff_t)p * G, -stride, 2, up);
-            if (down >= 1) cs_add(acc, cc_lds128(u + NP * 256));
-            if (down >= 2) acc = cc_walk(acc, cbase + (ptrdiff_t)p * G, stride, 2, down);
+            if (up >= 1) cs_add(acc, cc_lds128(t - NP * 256));
+            if (up >= 2) acc = cc_far_rows(acc, cbase + (ptrdiff_t)p * G, -stride, up);
+            if (down >= 1) cs_add(acc, cc_lds128(t + NP * 256));
+            if (down >= 2) acc = cc_far_rows(acc, cbase + (ptrdiff_t)p * G, stride, down);
             cc_sts128(t, cc_divide(acc, __uint_as_float(pi.y), __uint_as_float(pi.z)));
         }
     }
     if (any_far) {
-        // rare: out_k of the halo pixels beyond the staged one, straight from global memory
+        // rare: out_k of the halo pixels beyond the staged one, straight from global memory, into the ends of the
+        // h-1 / h+1 buffers next to T (every warp is past its column phase after this barrier)
         if (far) { atomicMax(&reach[0], lneed); atomicMax(&reach[1], rneed); }
         __syncthreads();
-        const int nl = max(reach[0] - 1, 0), nr = max(reach[1] - 1, 0);
-        for (int it = tid; it < (nl + nr) * CS_GC; it += CC_THREADS) {
+        const int nl = max(reach[0] - HL, 0), nr = max(reach[1] - HL, 0);
+        for (int it = tid; it < (nl + nr) * CS_GC; it += C::NT) {
             const int q = it >> 4;
-            const int fx = q < nl ? -2 - q : S + 1 + (q - nl);                     // segment-relative column
+            const int fx = q < nl ? -HL - 1 - q : S + HL + (q - nl);               // segment-relative column
             const int x = w0 + fx;
             if (!gok || x < 0 || x >= W) continue;
             const uchar4 a = arms[rowp + x];
@@ -168,7 +189,7 @@ __global__ void __launch_bounds__(CC_THREADS, CC_MIN_BLOCKS) k_cbca_colrow(const
             cs_add(acc, c[0]);
             acc = cc_walk(acc, c, -stride, 1, a.x);
             acc = cc_walk(acc, c, stride, 1, a.y);
-            cc_sts128(sT + (HM + fx) * 256 + my, cc_divide(acc, n, 1.0f / n));
+            cc_sts128(sT + (fx + HL) * 256 + my, cc_divide(acc, n, 1.0f / n));
         }
     }
     __syncthreads();
@@ -177,7 +198,7 @@ __global__ void __launch_bounds__(CC_THREADS, CC_MIN_BLOCKS) k_cbca_colrow(const
     if (gok) {
         char *out = reinterpret_cast<char *>(dst + (rowp + w0 + slot) * G + g);
         const ptrdiff_t stepB = (ptrdiff_t)SLOTS * G * 16;
-        unsigned t0 = sT + (HM + slot) * 256 + my, pa = sP + (slot + 1) * 16;
+        unsigned t0 = sT + (slot + HL) * 256 + my, pa = sP + (slot + HL) * 16;
 #pragma unroll 1
         for (int px = slot; px < sv; px += SLOTS, t0 += SLOTS * 256, pa += SLOTS * 16, out += stepB) {
             unsigned a;
