@@ -3,8 +3,9 @@
 ``StereoMatcher`` owns every device buffer a pair of shape (H, W, ndisp) needs (allocated once
 with torch), and ``run`` issues the hot path -- features, cost volume, CBCA x iters1, four chained
 SGM passes, CBCA x iters2, WTA, LR-check/interpolation, sub-pixel, median, bilateral -- as a fixed
-sequence of C-ABI calls on the current CUDA stream: no allocation, no host synchronisation and no
-host<->device traffic inside.  ``run_host`` is the same with NumPy images in / NumPy disparity out
+sequence of C-ABI calls on the current CUDA stream: no allocation and no host<->device traffic inside, and one host
+synchronisation (a number per image read back after the cross arms to choose between the two bit-identical
+aggregation schedules; none when `cbca_mode` is given explicitly).  ``run_host`` is the same with NumPy images in / NumPy disparity out
 through pinned staging buffers (what match.py's loop body amounts to end to end).
 
 Hyper-parameter defaults are match.py:32-43.
@@ -72,6 +73,7 @@ class StereoMatcher(object):
         self.h2d_bytes = 2 * H * W * 4
         self.d2h_bytes = H * W * 4
         self.cbca_mode = _pf.CBCA_MODE if cbca_mode is None else int(cbca_mode)
+        self.cbca_modes = [_pf.CBCA_SEPARABLE if self.cbca_mode == _pf.CBCA_AUTO else self.cbca_mode] * 2
         self.final_volume = None        # HWD left volume the last run's WTA / sub-pixel read
         self.result = None
         self._steps = self._build()
@@ -111,13 +113,16 @@ class StereoMatcher(object):
                 for i in range(2):
                     call("mccnn_cross_arms", p(img[i]), p(self.arms[i]), p(self.count[i]), H, W,
                          f(np.float32(hp["cbca_intensity"])), int(hp["cbca_distance"]), sp())
+                    # chained rounds or two passes per round: bit-identical, chosen per image from its arms (one number
+                    # read back from the device: the only host synchronisation of the step)
+                    self.cbca_modes[i] = _pf.cbca_auto_mode(self.arms[i]) if self.cbca_mode == _pf.CBCA_AUTO else self.cbca_mode
             return arms
 
         def make_cbca(src, dst, iters):
             def cbca():
                 for i in range(2):
                     call("mccnn_cbca", p(src[i]), p(dst[i]), p(self.volS), p(self.arms[i]), p(self.count[i]), D, H, W,
-                         iters, int(hp["cbca_distance"]), int(self.cbca_mode), sp())
+                         iters, int(hp["cbca_distance"]), int(self.cbca_modes[i]), sp())
             return cbca
 
         def make_sgm(vol):

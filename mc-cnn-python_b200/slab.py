@@ -272,6 +272,7 @@ class SlabRank(object):
         self.labels = e(H, W, dtype=torch.int32)
         self.table = _pf._to_dev(_pf.bilateral_table(5, 5, 0, self.hp["blur_sigma"]))
         self.cbca_mode = _pf.CBCA_MODE if cbca_mode is None else int(cbca_mode)
+        self.cbca_modes = [_pf.CBCA_SEPARABLE if self.cbca_mode == _pf.CBCA_AUTO else self.cbca_mode] * 2
         self.result = None
 
     def set_images(self, left_image, right_image):
@@ -306,9 +307,11 @@ class SlabRank(object):
         for i in range(2):
             call("mccnn_cross_arms", p(self.img[i]), p(self.arms[i]), p(self.count[i]), H, W,
                  ctypes.c_float(np.float32(hp["cbca_intensity"])), int(hp["cbca_distance"]), sp())
+            # (every rank sees the same images, so every rank makes the same choice)
+            self.cbca_modes[i] = _pf.cbca_auto_mode(self.arms[i]) if self.cbca_mode == _pf.CBCA_AUTO else self.cbca_mode
         it1 = int(hp["cbca_num_iterations1"])
-        # the fused hand-over exists for the default summation order only: another mode aggregates in place and pushes
-        if bases is None or it1 < 1 or self.cbca_mode != _pf.CBCA_SEPARABLE:
+        # the fused hand-over exists for the chained separable rounds only: another mode aggregates in place and pushes
+        if bases is None or it1 < 1 or any(m != _pf.CBCA_SEPARABLE for m in self.cbca_modes):
             for v in range(2):
                 self._cbca(v, self.volA, self.volB, it1)
             if bases is not None:
@@ -324,7 +327,7 @@ class SlabRank(object):
     def _cbca(self, i, src, dst, iters):
         p, call, sp, hp, pl = _ffi.ptr, _ffi.call, _ffi.stream_ptr, self.hp, self.plan
         call("mccnn_cbca", p(src[i]), p(dst[i]), p(self.volS), p(self.arms[i]), p(self.count[i]), self.Dl, pl.H, pl.W,
-             iters, int(hp["cbca_distance"]), int(self.cbca_mode), sp())
+             iters, int(hp["cbca_distance"]), int(self.cbca_modes[i]), sp())
 
     def _views(self, flat, shapes):
         out, off = [], 0

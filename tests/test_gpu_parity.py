@@ -216,7 +216,7 @@ def test_cbca_bit_exact_vs_oracle(pf, oracle, H, W, D, levels, iters, exact_cbca
 def test_cbca_separable_vs_golden_and_oracle(pf, oracle, pipeline_golden):
     """Default (separable) mode: same region, same order within rows and along the spine, row sums
     formed first -> equal to the reference up to float32 re-association."""
-    assert pf.CBCA_MODE == pf.CBCA_SEPARABLE
+    assert pf.CBCA_MODE == pf.CBCA_AUTO           # chained rounds or two passes per round, chosen per image; same bits
     g = pipeline_golden
 
     def close(a, b):
@@ -289,6 +289,26 @@ def test_cbca_chained_rounds_match_two_pass(pf, monkeypatch):
         monkeypatch.setattr(pf, "CBCA_MODE", pf.CBCA_SEPARABLE)
         Lt, Rt = pf.cost_volume_aggregation(li, ri, Lv, Rv, 0.02, dist, iters)
         assert eq(Ls, Lt) and eq(Rs, Rt), (H, W, D, levels, iters, dist)
+
+
+def test_cbca_auto_mode_follows_the_vertical_arms(pf, pkg):
+    """The host-side default picks the chained rounds for natural images and two passes per round when the vertical arms
+    are long (piece-wise constant images); either way the bits are the same."""
+    import torch
+    from bench import synth_pair, flat_pair
+    H, W, D = 96, 256, 24
+    for maker, want in ((synth_pair, pf.CBCA_SEPARABLE), (flat_pair, pf.CBCA_SEPARABLE_TWO_PASS)):
+        li, ri = maker(H, W, 9, seed=2)
+        arms, _ = pf.cross_arms(li, 0.02, 14)
+        assert pf.cbca_auto_mode(arms) == want
+        m = pkg.StereoMatcher(H, W, D)
+        m.set_images(li, ri)
+        d_auto = m.run().clone()
+        assert m.cbca_modes[0] == want
+        for mode in (pf.CBCA_SEPARABLE, pf.CBCA_SEPARABLE_TWO_PASS):
+            e = pkg.StereoMatcher(H, W, D, cbca_mode=mode)
+            e.set_images(li, ri)
+            assert torch.equal(e.run(), d_auto), mode
 
 
 def test_cbca_every_mode_with_long_arms(pf, oracle, monkeypatch):
