@@ -482,7 +482,7 @@ def run_ours(args):
                 acc[k] = acc.get(k, 0.0) + v / reps
     # worst case for the aggregation: the same step on a piece-wise constant pair, every arm at its limit
     acc_flat = {}
-    if rank == 0 and world == 1 and full and args.image != "flat" and not single_pair:
+    if rank == 0 and world == 1 and full and args.image != "flat" and not single_pair and not args.no_flat_stage:
         m.set_images(*flat_pair(H, W, min(37, D // 4), seed=0))
         m.run()
         for _ in range(reps):
@@ -591,6 +591,7 @@ def main():
     ap.add_argument("--image", default="natural", choices=["natural", "flat"],
                     help="flat: piece-wise constant pair, every cross arm at its limit (worst case for the aggregation)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-flat-stage", action="store_true", help="skip the extra passes on the piece-wise constant image")
     ap.add_argument("--no-extra-legs", action="store_true", help="with --gpus N > 1: skip the slab (c5) and c4 legs")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -64,7 +64,9 @@ int mccnn_features(const float *img, int H, int W, int pad, int num_layers,
                    float *out, void *scratch, void *stream);
 
 /* ---- a3  pf:78 compute_cost_volume ----
- * fl, fr [H][W][C]; L, R: HWD volumes.  Requires C == 64, D >= 1, W >= D + 2. */
+ * fl, fr [H][W][C]; L, R: HWD volumes.  Requires C == 64, 1 <= D <= 512 (a limit the reference does not have: the
+ * band of one tile and the SGM register tiling are sized for it; more disparities go through the slab entry points
+ * below), W >= D + 2. */
 int mccnn_cost_volume(const float *fl, const float *fr, float *L, float *R,
                       int H, int W, int C, int D, void *stream);
 
@@ -99,7 +101,7 @@ int mccnn_cbca(const float *in, float *out, float *scratch, const uint8_t *arms,
 /* ---- a6  pf:476 semi_global_matching, one in-place pass over one volume ----
  * (rh, rw) in {(0,1),(0,-1),(-1,0),(1,0)}.  P1/P2/Q1/Q2/tauD arrive as doubles and are rounded to
  * float32 exactly where the reference rounds them (pf:504-505, :538-541).
- * flags_scratch: mccnn_sgm_scratch_bytes(H, W, D) bytes. */
+ * flags_scratch: mccnn_sgm_scratch_bytes(H, W, D) bytes.  D <= 512 (MCCNN_ERR_UNSUPPORTED above). */
 size_t mccnn_sgm_scratch_bytes(int H, int W, int D);
 int mccnn_sgm_pass(float *vol, const float *img_left, const float *img_right, void *flags_scratch,
                    int D, int H, int W, int rh, int rw,

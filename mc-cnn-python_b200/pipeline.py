@@ -42,6 +42,7 @@ class StereoMatcher(object):
             assert s in STAGES, "unknown stage %r" % s
         H, W, D = self.H, self.W, self.D
         assert D >= 2 and W >= D + 2, "need ndisp >= 2 and W >= ndisp + 2 (pf:94-95, :547-566)"
+        assert D <= 512, "ndisp > 512 is not supported by one call (include/mccnn_b200.h); use slab.SlabMatcher"
         dev = _pf._dev()
         self.device = dev
         f32 = torch.float32
