@@ -7,6 +7,7 @@
 // HWD layout makes that walk cheap: the lanes of a warp are the disparities of one or two
 // pixels, so every lane follows the same arms (no divergence) and every load is a contiguous
 // 16 B granule of the neighbour pixel's disparity row (fully coalesced for any region shape).
+#include <stdlib.h>
 #include "common.cuh"
 #include "cbca_stream.cuh"
 #include "cbca_chain.cuh"
@@ -151,10 +152,32 @@ static int launch_colrow_shape(const float *hs_in, float *hs_out, const uint8_t 
     return MCCNN_OK;
 }
 
+template <class C>
+static int launch_colrow_tma_shape(const CUtensorMap &map, const float *hs_in, float *hs_out, const uint8_t *arms, const int32_t *count,
+                                   int G, int H, int W, cudaStream_t s) {
+    MCCNN_CUDA(cudaFuncSetAttribute(k_cbca_colrow_tma<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
+    dim3 grid(cdiv(G, CS_GC), cdiv(W, C::S), H);
+    k_cbca_colrow_tma<C><<<grid, C::NT, C::SMEM, s>>>(map, reinterpret_cast<const float4 *>(hs_in), reinterpret_cast<float4 *>(hs_out),
+                                                      reinterpret_cast<const uchar4 *>(arms), count, G, H, W);
+    MCCNN_LAUNCHED("cbca_colrow_tma");
+    return MCCNN_OK;
+}
+
+// experiment switch (read once): MCCNN_CBCA_CHAIN = 0 cp.async narrow (r2 default), 1 TMA narrow, 2 TMA wide, 3 cp.async wide
+static int chain_variant() {
+    static int v = -1;
+    if (v < 0) { const char *e = getenv("MCCNN_CBCA_CHAIN"); v = e ? atoi(e) : 1; }
+    return v;
+}
+
 // Measured at C3, ms per round of a 16-round call (natural / piece-wise constant image): CcNarrow 0.438 / 2.65,
 // CcWide 0.448 / 2.38, CcNarrow with two staged halo pixels per side 0.451 / 2.78, two streaming passes 0.580 / 1.85.
-static int launch_colrow(const float *hs_in, float *hs_out, const uint8_t *arms, const int32_t *count, int G, int H, int W,
-                         cudaStream_t s) {
+static int launch_colrow(const CUtensorMap *map, const float *hs_in, float *hs_out, const uint8_t *arms, const int32_t *count, int G,
+                         int H, int W, cudaStream_t s) {
+    const int v = chain_variant();
+    if (map && v == 1) return launch_colrow_tma_shape<CcNarrow>(*map, hs_in, hs_out, arms, count, G, H, W, s);
+    if (map && v == 2) return launch_colrow_tma_shape<CcWide>(*map, hs_in, hs_out, arms, count, G, H, W, s);
+    if (v == 3) return launch_colrow_shape<CcWide>(hs_in, hs_out, arms, count, G, H, W, s);
     return launch_colrow_shape<CcNarrow>(hs_in, hs_out, arms, count, G, H, W, s);
 }
 
@@ -169,8 +192,18 @@ static int chained_rounds(const float *in, float *out, float *scratch, const CsS
     k_cbca_pass<false, CS_ITEMS, 1><<<grid, CS_THREADS, 0, s>>>(reinterpret_cast<const float4 *>(in), reinterpret_cast<float4 *>(hs[0]),
                                                                 reinterpret_cast<const uchar4 *>(arms), count, G, H, W);
     MCCNN_LAUNCHED("cbca_rows");
+    // tensor maps of the two row-sum buffers for the TMA load of k_cbca_colrow_tma: {Dp, W, H}, box {64, NP, 3}
+    CUtensorMap maps[2];
+    const int v = chain_variant();
+    const bool use_tma = v == 1 || v == 2;
+    if (use_tma)
+        for (int b = 0; b < 2 && b < iters - 1; b++) {
+            int rc = tc_encode_map_3d(maps[b], hs[b], (unsigned long long)G * 4, W, H, CS_GC * 4, v == 2 ? CcWide::NP : CcNarrow::NP,
+                                      false, "cbca", 3);
+            if (rc) return rc;
+        }
     for (int k = 1; k < iters; k++) {
-        int rc = launch_colrow(hs[(k - 1) & 1], hs[k & 1], arms, count, G, H, W, s);
+        int rc = launch_colrow(use_tma ? &maps[(k - 1) & 1] : nullptr, hs[(k - 1) & 1], hs[k & 1], arms, count, G, H, W, s);
         if (rc) return rc;
     }
     if (!sc) {

@@ -22,6 +22,7 @@
 // Same additions in the same order as the two-pass form => bit-identical to it (tests: *_match_two_pass).
 #pragma once
 #include "cbca_stream.cuh"
+#include "tc_common.cuh"
 
 namespace mccnn {
 
@@ -96,6 +97,96 @@ __device__ __forceinline__ float4 cc_far_rows(float4 acc, const float4 *__restri
     return acc;
 }
 
+// ---- the three phases after the load, shared by the two kernels below (they differ in how the rows get into shared memory)
+
+// column phase: out_k of the staged pixels p = slot, slot + SLOTS, ..  (p_lo <= p < np) into T
+template <class C>
+__device__ __forceinline__ void cc_column_phase(const float4 *__restrict__ cbase, const ptrdiff_t stride, const int G, const unsigned sT,
+                                                const unsigned sP, const unsigned my, const int slot, const int p_lo, const int np) {
+    constexpr int NP = C::NP, SLOTS = C::SLOTS;
+    unsigned t = sT + slot * 256 + my, pa = sP + slot * 16;
+#pragma unroll 1
+    for (int p = slot; p < np; p += SLOTS, t += SLOTS * 256, pa += SLOTS * 16) {
+        if (p < p_lo) continue;
+        const uint4 pi = cc_lds128u(pa);
+        const int up = pi.x & 0xff, down = (pi.x >> 8) & 0xff;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        cs_add(acc, cc_lds128(t));                                             // h, h-1, .., h-up, then h+1, .., h+down
+        if (up >= 1) cs_add(acc, cc_lds128(t - NP * 256));
+        if (up >= 2) acc = cc_far_rows(acc, cbase + (ptrdiff_t)p * G, -stride, up);
+        if (down >= 1) cs_add(acc, cc_lds128(t + NP * 256));
+        if (down >= 2) acc = cc_far_rows(acc, cbase + (ptrdiff_t)p * G, stride, down);
+        cc_sts128(t, cc_divide(acc, __uint_as_float(pi.y), __uint_as_float(pi.z)));
+    }
+}
+
+// rare: out_k of the halo pixels beyond the staged one, straight from global memory, into the ends of the
+// h-1 / h+1 buffers next to T (every warp is past its column phase when this runs)
+template <class C>
+__device__ __forceinline__ void cc_far_halo(const float4 *__restrict__ src, const uchar4 *__restrict__ arms,
+                                            const int32_t *__restrict__ count, const int nl, const int nr, const int tid,
+                                            const bool gok, const int g, const int G, const int W, const int w0, const size_t rowp,
+                                            const ptrdiff_t stride, const unsigned sT, const unsigned my) {
+    constexpr int S = C::S, HL = C::HL;
+    for (int it = tid; it < (nl + nr) * CS_GC; it += C::NT) {
+        const int q = it >> 4;
+        const int fx = q < nl ? -HL - 1 - q : S + HL + (q - nl);               // segment-relative column
+        const int x = w0 + fx;
+        if (!gok || x < 0 || x >= W) continue;
+        const uchar4 a = arms[rowp + x];
+        const float n = (float)count[rowp + x];
+        const float4 *c = src + (rowp + x) * G + g;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        cs_add(acc, c[0]);
+        acc = cc_walk(acc, c, -stride, 1, a.x);
+        acc = cc_walk(acc, c, stride, 1, a.y);
+        cc_sts128(sT + (fx + HL) * 256 + my, cc_divide(acc, n, 1.0f / n));
+    }
+}
+
+// row phase: Hs_{k+1} of the segment from shared memory
+template <class C>
+__device__ __forceinline__ void cc_row_phase(float4 *__restrict__ dst, const size_t rowp, const int w0, const int g, const int G,
+                                             const unsigned sT, const unsigned sP, const unsigned my, const int slot, const int sv) {
+    constexpr int SLOTS = C::SLOTS, HL = C::HL;
+    char *out = reinterpret_cast<char *>(dst + (rowp + w0 + slot) * G + g);
+    const ptrdiff_t stepB = (ptrdiff_t)SLOTS * G * 16;
+    unsigned t0 = sT + (slot + HL) * 256 + my, pa = sP + (slot + HL) * 16;
+#pragma unroll 1
+    for (int px = slot; px < sv; px += SLOTS, t0 += SLOTS * 256, pa += SLOTS * 16, out += stepB) {
+        unsigned a;
+        asm volatile("ld.shared.u32 %0, [%1];\n" : "=r"(a) : "r"(pa));
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        cs_add(acc, cc_lds128(t0));                                            // w, w-1, .., w-left, then w+1, .., w+right
+        const unsigned tl = t0 - ((a >> 16) & 0xff) * 256, tr = t0 + (a >> 24) * 256;
+#pragma unroll 1
+        for (unsigned t = t0; t != tl;) { t -= 256; cs_add(acc, cc_lds128(t)); }
+#pragma unroll 1
+        for (unsigned t = t0; t != tr;) { t += 256; cs_add(acc, cc_lds128(t)); }
+        *reinterpret_cast<float4 *>(out) = acc;
+    }
+}
+
+// per-pixel information, one thread per staged pixel: (arms, |U|, RN(1/|U|)) into shared memory; returns whether some row
+// arm of the segment leaves the staged halo (and how far, in lneed / rneed)
+template <class C>
+__device__ __forceinline__ bool cc_pixel_info(const uchar4 *__restrict__ arms, const int32_t *__restrict__ count, const size_t rowp,
+                                              const int w0, const int tid, const int p_lo, const int np, const int sv,
+                                              const unsigned sP, int &lneed, int &rneed) {
+    constexpr int HL = C::HL;
+    lneed = 0; rneed = 0;
+    if (tid >= p_lo && tid < np) {
+        const size_t q = rowp + w0 - HL + tid;
+        const uchar4 a = arms[q];
+        const float n = (float)count[q];
+        cc_sts128u(sP + tid * 16, make_uint4((unsigned)a.x | (unsigned)a.y << 8 | (unsigned)a.z << 16 | (unsigned)a.w << 24,
+                                             __float_as_uint(n), __float_as_uint(1.0f / n), 0u));
+        const int px = tid - HL;
+        if (px >= 0 && px < sv) { lneed = (int)a.z - px; rneed = (int)a.w - (sv - 1 - px); }
+    }
+    return lneed > HL || rneed > HL;
+}
+
 template <class C>
 __global__ void __launch_bounds__(C::NT, C::MINB) k_cbca_colrow(const float4 *__restrict__ src, float4 *__restrict__ dst,
                                                                 const uchar4 *__restrict__ arms, const int32_t *__restrict__ count,
@@ -137,82 +228,68 @@ __global__ void __launch_bounds__(C::NT, C::MINB) k_cbca_colrow(const float4 *__
             }
         }
     }
-    // ---- per-pixel information, one thread per staged pixel; does some row arm of the segment leave the staged halo?
-    int lneed = 0, rneed = 0;
-    if (tid >= p_lo && tid < np) {
-        const size_t q = rowp + w0 - HL + tid;
-        const uchar4 a = arms[q];
-        const float n = (float)count[q];
-        cc_sts128u(sP + tid * 16, make_uint4((unsigned)a.x | (unsigned)a.y << 8 | (unsigned)a.z << 16 | (unsigned)a.w << 24,
-                                             __float_as_uint(n), __float_as_uint(1.0f / n), 0u));
-        const int px = tid - HL;
-        if (px >= 0 && px < sv) { lneed = (int)a.z - px; rneed = (int)a.w - (sv - 1 - px); }
-    }
-    const bool far = lneed > HL || rneed > HL;
+    int lneed, rneed;
+    const bool far = cc_pixel_info<C>(arms, count, rowp, w0, tid, p_lo, np, sv, sP, lneed, rneed);
     // (the barrier only publishes the per-pixel information: it comes BEFORE the wait for the staged rows, so that a warp
     //  whose own rows have arrived does not wait for the slowest warp's)
     const int any_far = __syncthreads_or(far);
     asm volatile("cp.async.wait_all;\n" ::: "memory");
 
-    // ---- column phase: out_k of the staged pixels, each thread in the slots it loaded itself
-    if (gok) {
-        unsigned t = sT + slot * 256 + my, pa = sP + slot * 16;
-#pragma unroll 1
-        for (int p = slot; p < np; p += SLOTS, t += SLOTS * 256, pa += SLOTS * 16) {
-            if (p < p_lo) continue;
-            const uint4 pi = cc_lds128u(pa);
-            const int up = pi.x & 0xff, down = (pi.x >> 8) & 0xff;
-            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-            cs_add(acc, cc_lds128(t));                                             // h, h-1, .., h-up, then h+1, .., h+down
-            if (up >= 1) cs_add(acc, cc_lds128(t - NP * 256));
-            if (up >= 2) acc = cc_far_rows(acc, cbase + (ptrdiff_t)p * G, -stride, up);
-            if (down >= 1) cs_add(acc, cc_lds128(t + NP * 256));
-            if (down >= 2) acc = cc_far_rows(acc, cbase + (ptrdiff_t)p * G, stride, down);
-            cc_sts128(t, cc_divide(acc, __uint_as_float(pi.y), __uint_as_float(pi.z)));
-        }
-    }
+    if (gok) cc_column_phase<C>(cbase, stride, G, sT, sP, my, slot, p_lo, np);   // each thread in the slots it loaded itself
     if (any_far) {
-        // rare: out_k of the halo pixels beyond the staged one, straight from global memory, into the ends of the
-        // h-1 / h+1 buffers next to T (every warp is past its column phase after this barrier)
         if (far) { atomicMax(&reach[0], lneed); atomicMax(&reach[1], rneed); }
         __syncthreads();
-        const int nl = max(reach[0] - HL, 0), nr = max(reach[1] - HL, 0);
-        for (int it = tid; it < (nl + nr) * CS_GC; it += C::NT) {
-            const int q = it >> 4;
-            const int fx = q < nl ? -HL - 1 - q : S + HL + (q - nl);               // segment-relative column
-            const int x = w0 + fx;
-            if (!gok || x < 0 || x >= W) continue;
-            const uchar4 a = arms[rowp + x];
-            const float n = (float)count[rowp + x];
-            const float4 *c = src + (rowp + x) * G + g;
-            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-            cs_add(acc, c[0]);
-            acc = cc_walk(acc, c, -stride, 1, a.x);
-            acc = cc_walk(acc, c, stride, 1, a.y);
-            cc_sts128(sT + (fx + HL) * 256 + my, cc_divide(acc, n, 1.0f / n));
-        }
+        cc_far_halo<C>(src, arms, count, max(reach[0] - HL, 0), max(reach[1] - HL, 0), tid, gok, g, G, W, w0, rowp, stride, sT, my);
     }
     __syncthreads();
+    if (gok) cc_row_phase<C>(dst, rowp, w0, g, G, sT, sP, my, slot, sv);
+}
 
-    // ---- row phase: Hs_{k+1} of the segment from shared memory
-    if (gok) {
-        char *out = reinterpret_cast<char *>(dst + (rowp + w0 + slot) * G + g);
-        const ptrdiff_t stepB = (ptrdiff_t)SLOTS * G * 16;
-        unsigned t0 = sT + (slot + HL) * 256 + my, pa = sP + (slot + HL) * 16;
-#pragma unroll 1
-        for (int px = slot; px < sv; px += SLOTS, t0 += SLOTS * 256, pa += SLOTS * 16, out += stepB) {
-            unsigned a;
-            asm volatile("ld.shared.u32 %0, [%1];\n" : "=r"(a) : "r"(pa));
-            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-            cs_add(acc, cc_lds128(t0));                                            // w, w-1, .., w-left, then w+1, .., w+right
-            const unsigned tl = t0 - ((a >> 16) & 0xff) * 256, tr = t0 + (a >> 24) * 256;
-#pragma unroll 1
-            for (unsigned t = t0; t != tl;) { t -= 256; cs_add(acc, cc_lds128(t)); }
-#pragma unroll 1
-            for (unsigned t = t0; t != tr;) { t += 256; cs_add(acc, cc_lds128(t)); }
-            *reinterpret_cast<float4 *>(out) = acc;
-        }
+// The same round with the load done by the TMA unit: ONE cp.async.bulk.tensor per CTA brings the 3 rows x NP pixels x 64
+// disparities box (24 KB) of Hs_k; cells outside the volume (image borders, granules beyond Dp) arrive as zeros and are never
+// used.  Removes the per-thread load loop (12 cp.async with their 64-bit addresses and predicates, a sixth of the kernel's
+// instructions); the rows are published by an mbarrier instead of cp.async.wait_all.
+// map: float32 tensor {Dp, W, H} of src, box {64, NP, 3}, no swizzle.
+template <class C>
+__global__ void __launch_bounds__(C::NT, C::MINB) k_cbca_colrow_tma(const __grid_constant__ CUtensorMap map, const float4 *__restrict__ src,
+                                                                    float4 *__restrict__ dst, const uchar4 *__restrict__ arms,
+                                                                    const int32_t *__restrict__ count, int G, int H, int W) {
+    constexpr int S = C::S, NP = C::NP, HL = C::HL;
+    extern __shared__ __align__(128) unsigned char cc_raw[];
+    __shared__ int reach[2];
+    __shared__ __align__(8) unsigned long long bar;
+    const unsigned sU = (unsigned)__cvta_generic_to_shared(cc_raw);
+    const unsigned sT = sU + NP * 256, sP = sU + 3 * NP * 256;
+    const int tid = threadIdx.x, gi = tid & 15, slot = tid >> 4;
+    const int g = blockIdx.x * CS_GC + gi, w0 = blockIdx.y * S, h = blockIdx.z;
+    if (tid == 0) {
+        tc_mbar_init(&bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+        tc_mbar_expect_tx(&bar, 3 * NP * 256);
+        tc_tma_load_3d(cc_raw, &map, blockIdx.x * (CS_GC * 4), w0 - HL, h - 1, &bar);
+        reach[0] = 0; reach[1] = 0;
     }
+    const bool gok = g < G;
+    const int sv = min(S, W - w0);
+    const int np = min(NP, W - w0 + HL);
+    const int p_lo = w0 > 0 ? 0 : HL;
+    const ptrdiff_t stride = (ptrdiff_t)W * G;
+    const size_t rowp = (size_t)h * W;
+    const float4 *cbase = src + (rowp + w0 - HL) * G + g;
+    const unsigned my = gi * 16;
+    int lneed, rneed;
+    const bool far = cc_pixel_info<C>(arms, count, rowp, w0, tid, p_lo, np, sv, sP, lneed, rneed);
+    const int any_far = __syncthreads_or(far);                        // publishes the per-pixel information and the mbarrier
+    tc_mbar_wait(&bar, 0);
+
+    if (gok) cc_column_phase<C>(cbase, stride, G, sT, sP, my, slot, p_lo, np);
+    if (any_far) {
+        if (far) { atomicMax(&reach[0], lneed); atomicMax(&reach[1], rneed); }
+        __syncthreads();
+        cc_far_halo<C>(src, arms, count, max(reach[0] - HL, 0), max(reach[1] - HL, 0), tid, gok, g, G, W, w0, rowp, stride, sT, my);
+    }
+    __syncthreads();
+    if (gok) cc_row_phase<C>(dst, rowp, w0, g, G, sT, sP, my, slot, sv);
 }
 
 }  // namespace mccnn

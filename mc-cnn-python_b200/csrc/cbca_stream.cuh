@@ -11,6 +11,7 @@
 // Summation order inside a row and along the spine is the reference's; only the association
 // (row sums first) differs: ~1e-7 relative.
 #pragma once
+#include <math_constants.h>
 #include "common.cuh"
 
 namespace mccnn {
@@ -55,10 +56,26 @@ struct CsScatter {
     float4 *base[CS_MAX_PARTS];
 };
 
-template <bool COLS, int ITEMS, int NB, bool SC = false>
+// Winner-take-all (pf:239-272) folded into the closing column pass of an aggregation: the 16 lanes that share a pixel
+// reduce their first minimum over the 64 disparities the CTA holds and merge it into a per-pixel 64-bit key
+// (order-preserving image of the cost << 32 | disparity) with one atomicMin per (pixel, granule group); the smallest
+// key is the smallest cost and, among equal costs, the lowest disparity: np.argmin's first-minimum rule.  Saves
+// re-reading the volume (4 B per cell).  keys must be preset to all ones; k_wta_decode turns them into the map.
+struct CsWta {
+    unsigned long long *keys;     // [H * W]
+    int D;                        // disparities that exist (the pitch G * 4 may be larger)
+    int store;                    // 0: the aggregated volume itself is not needed afterwards (right volume of match.py)
+};
+__device__ __forceinline__ unsigned cs_fkey(float f) {             // order-preserving: a < b  <=>  key(a) < key(b)
+    const unsigned b = __float_as_uint(f);
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+
+template <bool COLS, int ITEMS, int NB, bool SC = false, bool WT = false>
 __global__ void __launch_bounds__(CS_THREADS, CS_MIN_BLOCKS) k_cbca_pass(const float4 *__restrict__ src, float4 *__restrict__ dst,
                                                           const uchar4 *__restrict__ arms, const int32_t *__restrict__ count,
-                                                          int G, int H, int W, const CsScatter sc = CsScatter()) {
+                                                          int G, int H, int W, const CsScatter sc = CsScatter(),
+                                                          const CsWta wt = CsWta()) {
     __shared__ float4 stage[2 * NB + 1][ITEMS][CS_THREADS];      // [centre, -1, +1, -2, +2, ..]
     constexpr int PH = 2 * ITEMS;
     // grid = (granule groups, patch columns, patch rows): the granule groups of a patch are consecutive CTAs, so a
@@ -116,6 +133,22 @@ __global__ void __launch_bounds__(CS_THREADS, CS_MIN_BLOCKS) k_cbca_pass(const f
                 acc = make_float4(acc.x / n[s], acc.y / n[s], acc.z / n[s], acc.w / n[s]);   // pf:161
             }
         }
+        if (WT) {
+            // this lane's first minimum (strict <, cells d >= D do not exist; NaN and +inf never win, as in k_wta)
+            const int d0 = g << 2;
+            float best = CUDART_INF_F;
+            int bd = 0;
+            if (acc.x < best) { best = acc.x; bd = d0; }
+            if (d0 + 1 < wt.D && acc.y < best) { best = acc.y; bd = d0 + 1; }
+            if (d0 + 2 < wt.D && acc.z < best) { best = acc.z; bd = d0 + 2; }
+            if (d0 + 3 < wt.D && acc.w < best) { best = acc.w; bd = d0 + 3; }
+            const unsigned half = 0xffffu << (threadIdx.x & 16);                   // the 16 lanes of this pixel
+            const unsigned k = best < CUDART_INF_F ? cs_fkey(best + 0.0f) : 0xffffffffu;   // (-0 counts as +0, like <)
+            const unsigned kmin = __reduce_min_sync(half, k);
+            const unsigned dmin = __reduce_min_sync(half, k == kmin ? (unsigned)bd : 0xffffffffu);
+            if (gi == 0 && kmin != 0xffffffffu) atomicMin(wt.keys + p[s], (unsigned long long)kmin << 32 | dmin);
+        }
+        if (WT && !wt.store) continue;
         if (!SC) {
             dst[p[s] * G + g] = acc;
         } else {
@@ -125,6 +158,14 @@ __global__ void __launch_bounds__(CS_THREADS, CS_MIN_BLOCKS) k_cbca_pass(const f
             sc.base[r][((size_t)(h - sc.lo[r]) * W + w) * sc.g_total + sc.g_off + g] = acc;
         }
     }
+}
+
+// map = disparity of the smallest key (-1 where no finite cost exists, like k_wta), optionally the cost itself
+__global__ void k_wta_decode(const unsigned long long *__restrict__ keys, float *__restrict__ disp, long long P) {
+    const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= P) return;
+    const unsigned long long k = keys[p];
+    disp[p] = k == ~0ull ? -1.0f : (float)(unsigned)(k & 0xffffffffu);
 }
 
 }  // namespace mccnn

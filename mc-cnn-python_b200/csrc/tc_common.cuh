@@ -128,9 +128,10 @@ typedef CUresult (*TcEncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32
                                     const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-// float32 tensor [d2][d1][d0] (d0 contiguous), box {b0, b1, 1}; swizzle128 = 128-byte swizzle (b0 * 4 must be 128)
+// float32 tensor [d2][d1][d0] (d0 contiguous), box {b0, b1, b2}; swizzle128 = 128-byte swizzle (b0 * 4 must be 128)
 static inline int tc_encode_map_3d(CUtensorMap &map, const float *base, unsigned long long d0, unsigned long long d1,
-                                   unsigned long long d2, unsigned b0, unsigned b1, bool swizzle128, const char *what) {
+                                   unsigned long long d2, unsigned b0, unsigned b1, bool swizzle128, const char *what,
+                                   unsigned b2 = 1) {
     static TcEncodeTiledFn enc = nullptr;
     if (!enc) {
         void *p = nullptr;
@@ -144,7 +145,7 @@ static inline int tc_encode_map_3d(CUtensorMap &map, const float *base, unsigned
     }
     const cuuint64_t gdim[3] = {d0, d1, d2};
     const cuuint64_t gstr[2] = {d0 * 4, d1 * d0 * 4};
-    const cuuint32_t box[3] = {b0, b1, 1};
+    const cuuint32_t box[3] = {b0, b1, b2};
     const cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = enc(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void *)base, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                      swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
