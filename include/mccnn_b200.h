@@ -62,6 +62,15 @@ size_t mccnn_features_scratch_bytes(int H, int W, int pad, int num_layers);
 int mccnn_features(const float *img, int H, int W, int pad, int num_layers,
                    const float *const *weights_host, const float *const *biases_host,
                    float *out, void *scratch, void *stream);
+/* The same with the network's constant part done once (the reference builds its graph once per process and runs it
+ * per image, pf:30-47): mccnn_features_prepare writes the hi/lo tf32 split of the weights of layers 2..n into
+ * `prepared` (mccnn_features_weights_bytes(num_layers) bytes, 32-byte aligned); mccnn_features_prepared uses it
+ * instead of splitting the weights on every call.  Same results bit for bit. */
+size_t mccnn_features_weights_bytes(int num_layers);
+int mccnn_features_prepare(int num_layers, const float *const *weights_host, void *prepared, void *stream);
+int mccnn_features_prepared(const float *img, int H, int W, int pad, int num_layers,
+                            const float *const *weights_host, const float *const *biases_host,
+                            const void *prepared, float *out, void *scratch, void *stream);
 
 /* ---- a3  pf:78 compute_cost_volume ----
  * fl, fr [H][W][C]; L, R: HWD volumes.  Requires C == 64, 1 <= D <= 512 (a limit the reference does not have: the
@@ -122,6 +131,16 @@ int mccnn_sgm_average_pair(float *vol_left, float *vol_right, const float *img_l
 
 /* ---- a8  pf:239 disparity_prediction, one volume: first minimum over d, stored as float32. */
 int mccnn_wta(const float *vol, float *disp, int D, int H, int W, void *stream);
+
+/* ---- a5 + a8 fused: match.py:155-160 runs disparity_prediction (pf:239) on the volume cost_volume_aggregation (pf:117)
+ * has just produced.  Same as mccnn_cbca (separable modes only) followed by mccnn_wta on `out`, but the closing column
+ * pass of the aggregation takes the first minimum itself, so the volume is not read again: disp [H][W] f32 is identical
+ * to mccnn_wta's (first minimum; -1 where no finite cost exists).  keys: scratch of H*W 8-byte words.  store_volume = 0
+ * additionally skips writing the aggregated volume (`out` then holds intermediate row sums; match.py never reads the
+ * right volume after its WTA, match.py:160-166); `out` and `scratch` are needed as work space either way. */
+int mccnn_cbca_wta(const float *in, float *out, float *scratch, const uint8_t *arms, const int32_t *count,
+                   int D, int H, int W, int iters, int distance_threshold, int mode, int store_volume,
+                   void *keys, float *disp, void *stream);
 
 /* ---- a9  pf:279 interpolation.  labels [H][W] i32 scratch/output (0 match, 1 mismatch, 2 occlusion). */
 int mccnn_lr_interp(const float *disp_left, const float *disp_right, float *out, int32_t *labels,

@@ -23,10 +23,14 @@ SIGNATURES = {
     "mccnn_hwd_to_dhw": (_i, [_vp, _vp, _i, _i, _i, _vp]),
     "mccnn_features_scratch_bytes": (_sz, [_i, _i, _i, _i]),
     "mccnn_features": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
+    "mccnn_features_weights_bytes": (_sz, [_i]),
+    "mccnn_features_prepare": (_i, [_i, _vp, _vp, _vp]),
+    "mccnn_features_prepared": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "mccnn_cost_volume": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "mccnn_cross_arms": (_i, [_vp, _vp, _vp, _i, _i, _f, _i, _vp]),
     "mccnn_cross_region_list": (_i, [_vp, _vp, _i, _i, _i, _vp]),
     "mccnn_cbca": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
+    "mccnn_cbca_wta": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
     "mccnn_sgm_scratch_bytes": (_sz, [_i, _i, _i]),
     "mccnn_sgm_pass": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _d, _d, _d, _d, _d, _i, _vp]),
     "mccnn_sgm_average": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _d, _d, _d, _d, _d, _d, _i, _vp]),

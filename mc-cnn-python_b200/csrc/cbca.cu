@@ -108,32 +108,46 @@ __global__ void __launch_bounds__(CBCA_THREADS) k_cbca_round(const float4 *__res
 }
 
 
+// The closing column pass of a separable call: plain, scattered to the row slabs of other ranks (sc), or with the
+// winner-take-all folded in (wt).
+static int closing_cols(const float *hs, float *out, const CsScatter *sc, const CsWta *wt, const uint8_t *arms, const int32_t *count,
+                        int G, int H, int W, cudaStream_t s) {
+    dim3 grid(cdiv(G, CS_GC), cdiv(W, CS_PW), cdiv(H, CS_PH));
+    const float4 *src = reinterpret_cast<const float4 *>(hs);
+    const uchar4 *a4 = reinterpret_cast<const uchar4 *>(arms);
+    if (wt) {
+        MCCNN_CUDA(cudaMemsetAsync(wt->keys, 0xff, (size_t)H * W * sizeof(unsigned long long), s));
+        k_cbca_pass<true, CS_ITEMS, 1, false, true><<<grid, CS_THREADS, 0, s>>>(src, reinterpret_cast<float4 *>(out), a4, count, G, H, W,
+                                                                               CsScatter(), *wt);
+        MCCNN_LAUNCHED("cbca_cols_wta");
+    } else if (sc) {
+        k_cbca_pass<true, CS_ITEMS, 1, true><<<grid, CS_THREADS, 0, s>>>(src, nullptr, a4, count, G, H, W, *sc);
+        MCCNN_LAUNCHED("cbca_cols_scatter");
+    } else {
+        k_cbca_pass<true, CS_ITEMS, 1><<<grid, CS_THREADS, 0, s>>>(src, reinterpret_cast<float4 *>(out), a4, count, G, H, W);
+        MCCNN_LAUNCHED("cbca_cols");
+    }
+    return MCCNN_OK;
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // One round of the separable mode: row sums src -> scratch, column sums scratch -> out (or scattered, sc != NULL).
-static int stream_round(const float *src, float *scratch, float *out, const CsScatter *sc, const uint8_t *arms,
+static int stream_round(const float *src, float *scratch, float *out, const CsScatter *sc, const CsWta *wt, const uint8_t *arms,
                         const int32_t *count, int G, int H, int W, cudaStream_t s) {
     dim3 grid(cdiv(G, CS_GC), cdiv(W, CS_PW), cdiv(H, CS_PH));
     k_cbca_pass<false, CS_ITEMS, 1><<<grid, CS_THREADS, 0, s>>>(reinterpret_cast<const float4 *>(src), reinterpret_cast<float4 *>(scratch),
                                                                 reinterpret_cast<const uchar4 *>(arms), count, G, H, W);
     MCCNN_LAUNCHED("cbca_rows");
-    if (!sc) {
-        k_cbca_pass<true, CS_ITEMS, 1><<<grid, CS_THREADS, 0, s>>>(reinterpret_cast<const float4 *>(scratch), reinterpret_cast<float4 *>(out),
-                                                                   reinterpret_cast<const uchar4 *>(arms), count, G, H, W);
-        MCCNN_LAUNCHED("cbca_cols");
-    } else {
-        k_cbca_pass<true, CS_ITEMS, 1, true><<<grid, CS_THREADS, 0, s>>>(reinterpret_cast<const float4 *>(scratch), nullptr,
-                                                                         reinterpret_cast<const uchar4 *>(arms), count, G, H, W, *sc);
-        MCCNN_LAUNCHED("cbca_cols_scatter");
-    }
-    return MCCNN_OK;
+    return closing_cols(scratch, out, sc, wt, arms, count, G, H, W, s);
 }
 
 // n >= 1 rounds as two streaming passes each; every round reads the previous round's `out`; the last column pass may scatter
-static int two_pass_rounds(const float *in, float *out, float *scratch, const CsScatter *sc, const uint8_t *arms,
+static int two_pass_rounds(const float *in, float *out, float *scratch, const CsScatter *sc, const CsWta *wt, const uint8_t *arms,
                            const int32_t *count, int G, int H, int W, int iters, cudaStream_t s) {
     const float *src = in;
     for (int it = 0; it < iters; it++) {
-        int rc = stream_round(src, scratch, out, (sc && it + 1 == iters) ? sc : nullptr, arms, count, G, H, W, s);
+        const bool last = it + 1 == iters;
+        int rc = stream_round(src, scratch, out, last ? sc : nullptr, last ? wt : nullptr, arms, count, G, H, W, s);
         if (rc) return rc;
         src = out;
     }
@@ -183,7 +197,7 @@ static int launch_colrow(const CUtensorMap *map, const float *hs_in, float *hs_o
 
 // n >= 2 rounds, chained: rows | (n-1) x colrow | cols.  The row sums ping-pong between `out` and `scratch` so that
 // the last ones sit in `scratch` and the closing column pass can write `out` (or scatter, sc != NULL).
-static int chained_rounds(const float *in, float *out, float *scratch, const CsScatter *sc, const uint8_t *arms,
+static int chained_rounds(const float *in, float *out, float *scratch, const CsScatter *sc, const CsWta *wt, const uint8_t *arms,
                           const int32_t *count, int G, int H, int W, int iters, cudaStream_t s) {
     dim3 grid(cdiv(G, CS_GC), cdiv(W, CS_PW), cdiv(H, CS_PH));
     float *hs[2];
@@ -206,23 +220,14 @@ static int chained_rounds(const float *in, float *out, float *scratch, const CsS
         int rc = launch_colrow(use_tma ? &maps[(k - 1) & 1] : nullptr, hs[(k - 1) & 1], hs[k & 1], arms, count, G, H, W, s);
         if (rc) return rc;
     }
-    if (!sc) {
-        k_cbca_pass<true, CS_ITEMS, 1><<<grid, CS_THREADS, 0, s>>>(reinterpret_cast<const float4 *>(scratch), reinterpret_cast<float4 *>(out),
-                                                                   reinterpret_cast<const uchar4 *>(arms), count, G, H, W);
-        MCCNN_LAUNCHED("cbca_cols");
-    } else {
-        k_cbca_pass<true, CS_ITEMS, 1, true><<<grid, CS_THREADS, 0, s>>>(reinterpret_cast<const float4 *>(scratch), nullptr,
-                                                                         reinterpret_cast<const uchar4 *>(arms), count, G, H, W, *sc);
-        MCCNN_LAUNCHED("cbca_cols_scatter");
-    }
-    return MCCNN_OK;
+    return closing_cols(scratch, out, sc, wt, arms, count, G, H, W, s);
 }
 
 // the default: chained rounds wherever they apply (two rounds or more; the shared-memory tile grows with the arm limit)
-static int separable_rounds(const float *in, float *out, float *scratch, const CsScatter *sc, const uint8_t *arms,
+static int separable_rounds(const float *in, float *out, float *scratch, const CsScatter *sc, const CsWta *wt, const uint8_t *arms,
                             const int32_t *count, int G, int H, int W, int iters, int hm, cudaStream_t s) {
-    if (iters >= 2 && CcNarrow::supports(hm)) return chained_rounds(in, out, scratch, sc, arms, count, G, H, W, iters, s);
-    return two_pass_rounds(in, out, scratch, sc, arms, count, G, H, W, iters, s);
+    if (iters >= 2 && CcNarrow::supports(hm)) return chained_rounds(in, out, scratch, sc, wt, arms, count, G, H, W, iters, s);
+    return two_pass_rounds(in, out, scratch, sc, wt, arms, count, G, H, W, iters, s);
 }
 
 }  // namespace mccnn
@@ -273,7 +278,30 @@ int mccnn_cbca_to(const float *in, float *out, float *scratch, const uint8_t *ar
         MCCNN_REQUIRE(row_bounds[r] < row_bounds[r + 1] && dst[r], "cbca_to: empty part or null destination %d", r);
         sc.base[r] = reinterpret_cast<float4 *>(dst[r]);
     }
-    return separable_rounds(in, out, scratch, &sc, arms, count, G, H, W, iters, dist - 1, (cudaStream_t)stream);
+    return separable_rounds(in, out, scratch, &sc, nullptr, arms, count, G, H, W, iters, dist - 1, (cudaStream_t)stream);
+}
+
+int mccnn_cbca_wta(const float *in, float *out, float *scratch, const uint8_t *arms, const int32_t *count, int D, int H, int W,
+                   int iters, int dist, int mode, int store_volume, void *keys, float *disp, void *stream) {
+    MCCNN_REQUIRE(mode == MCCNN_CBCA_SEPARABLE || mode == MCCNN_CBCA_SEPARABLE_TWO_PASS,
+                  "cbca_wta: mode %d has no fused winner-take-all (separable modes only)", mode);
+    MCCNN_REQUIRE(dist >= 1 && dist <= 255, "cbca_wta: distance_threshold %d outside [1, 255]", dist);
+    MCCNN_REQUIRE(in && out && scratch && arms && count && keys && disp && D >= 1 && H >= 1 && W >= 1 && iters >= 1,
+                  "cbca_wta: bad arguments");
+    MCCNN_REQUIRE(H <= 65535 && W <= 65535, "cbca_wta: image too large");
+    MCCNN_REQUIRE(in != out && scratch != in && scratch != out, "cbca_wta: in, out and scratch must differ");
+    MCCNN_REQUIRE(((uintptr_t)keys & 7) == 0, "cbca_wta: keys must be 8-byte aligned");
+    cudaStream_t s = (cudaStream_t)stream;
+    const int G = dpitch(D) / 4;
+    CsWta wt;
+    wt.keys = reinterpret_cast<unsigned long long *>(keys); wt.D = D; wt.store = store_volume != 0;
+    int rc = mode == MCCNN_CBCA_SEPARABLE ? separable_rounds(in, out, scratch, nullptr, &wt, arms, count, G, H, W, iters, dist - 1, s)
+                                          : two_pass_rounds(in, out, scratch, nullptr, &wt, arms, count, G, H, W, iters, s);
+    if (rc) return rc;
+    const long long P = (long long)H * W;
+    k_wta_decode<<<cdiv(P, 256), 256, 0, s>>>(wt.keys, disp, P);
+    MCCNN_LAUNCHED("wta_decode");
+    return MCCNN_OK;
 }
 
 int mccnn_cbca(const float *in, float *out, float *scratch, const uint8_t *arms, const int32_t *count, int D, int H,
@@ -293,8 +321,8 @@ int mccnn_cbca(const float *in, float *out, float *scratch, const uint8_t *arms,
         MCCNN_CUDA(cudaMemcpyAsync(out, in, (size_t)H * W * Dp * sizeof(float), cudaMemcpyDeviceToDevice, s));
         return MCCNN_OK;
     }
-    if (mode == MCCNN_CBCA_SEPARABLE) return separable_rounds(in, out, scratch, nullptr, arms, count, G, H, W, iters, dist - 1, s);
-    if (mode == MCCNN_CBCA_SEPARABLE_TWO_PASS) return two_pass_rounds(in, out, scratch, nullptr, arms, count, G, H, W, iters, s);
+    if (mode == MCCNN_CBCA_SEPARABLE) return separable_rounds(in, out, scratch, nullptr, nullptr, arms, count, G, H, W, iters, dist - 1, s);
+    if (mode == MCCNN_CBCA_SEPARABLE_TWO_PASS) return two_pass_rounds(in, out, scratch, nullptr, nullptr, arms, count, G, H, W, iters, s);
     // exact: ping-pong so that the last round lands in `out`
     float *buf[2];
     buf[(iters - 1) & 1] = out;

@@ -345,8 +345,23 @@ size_t mccnn_features_scratch_bytes(int H, int W, int pad, int num_layers) {
     return (2 * oh * ow * F + conv_weights_floats(num_layers)) * sizeof(float);
 }
 
-int mccnn_features(const float *img, int H, int W, int pad, int num_layers, const float *const *weights_host,
-                   const float *const *biases_host, float *out, void *scratch, void *stream) {
+size_t mccnn_features_weights_bytes(int num_layers) {
+    return num_layers >= 1 ? conv_weights_floats(num_layers) * sizeof(float) : 0;
+}
+
+int mccnn_features_prepare(int num_layers, const float *const *weights_host, void *prepared, void *stream) {
+    MCCNN_REQUIRE(weights_host && num_layers >= 1 && num_layers <= 16, "features_prepare: bad arguments");
+    MCCNN_REQUIRE(num_layers == 1 || (prepared && ((uintptr_t)prepared & 31) == 0), "features_prepare: prepared must be 32-byte aligned");
+    for (int l = 1; l < num_layers; l++) {
+        float *whi = (float *)prepared + (size_t)(l - 1) * 2 * 9 * F * F, *wlo = whi + 9 * F * F;
+        k_conv_prep_weights<<<cdiv(9 * F * F, 256), 256, 0, (cudaStream_t)stream>>>(weights_host[l], whi, wlo);
+        MCCNN_LAUNCHED("conv_prep_weights");
+    }
+    return MCCNN_OK;
+}
+
+static int features_impl(const float *img, int H, int W, int pad, int num_layers, const float *const *weights_host,
+                         const float *const *biases_host, const float *prepared, float *out, void *scratch, void *stream) {
     MCCNN_REQUIRE(img && weights_host && biases_host && out, "features: null pointer");
     MCCNN_REQUIRE(H >= 1 && W >= 1 && pad >= 0 && num_layers >= 1 && num_layers <= 16,
                   "features: bad shape H=%d W=%d pad=%d layers=%d", H, W, pad, num_layers);
@@ -359,7 +374,8 @@ int mccnn_features(const float *img, int H, int W, int pad, int num_layers, cons
     float *buf[2];
     buf[0] = (float *)scratch;
     buf[1] = buf[0] ? buf[0] + (size_t)oh * ow * F : nullptr;
-    float *wsplit = buf[0] ? buf[1] + (size_t)oh * ow * F : nullptr;
+    // the pre-split weights of layers 2..n: the caller's (mccnn_features_prepare, once per network), else made here
+    float *wsplit = prepared ? const_cast<float *>(prepared) : (buf[0] ? buf[1] + (size_t)oh * ow * F : nullptr);
     float *dst = (num_layers == 1) ? out : buf[0];
     {
         MCCNN_REQUIRE(oh <= 65535, "features: image too tall (%d rows)", oh);
@@ -387,8 +403,10 @@ int mccnn_features(const float *img, int H, int W, int pad, int num_layers, cons
         const bool last = (l == num_layers - 1);
         float *d = last ? out : buf[l & 1];
         float *whi = wsplit + (size_t)(l - 1) * 2 * 9 * F * F, *wlo = whi + 9 * F * F;
-        k_conv_prep_weights<<<cdiv(9 * F * F, 256), 256, 0, s>>>(weights_host[l], whi, wlo);
-        MCCNN_LAUNCHED("conv_prep_weights");
+        if (!prepared) {
+            k_conv_prep_weights<<<cdiv(9 * F * F, 256), 256, 0, s>>>(weights_host[l], whi, wlo);
+            MCCNN_LAUNCHED("conv_prep_weights");
+        }
         CtcMaps maps;
         int rc = tc_encode_map_3d(maps.in, src, F, iw, ih, 32, 128, true, "features");
         if (rc) return rc;
@@ -405,6 +423,17 @@ int mccnn_features(const float *img, int H, int W, int pad, int num_layers, cons
         src = d; ih = oh; iw = ow;
     }
     return MCCNN_OK;
+}
+
+int mccnn_features(const float *img, int H, int W, int pad, int num_layers, const float *const *weights_host,
+                   const float *const *biases_host, float *out, void *scratch, void *stream) {
+    return features_impl(img, H, W, pad, num_layers, weights_host, biases_host, nullptr, out, scratch, stream);
+}
+
+int mccnn_features_prepared(const float *img, int H, int W, int pad, int num_layers, const float *const *weights_host,
+                            const float *const *biases_host, const void *prepared, float *out, void *scratch, void *stream) {
+    MCCNN_REQUIRE(num_layers == 1 || (prepared && ((uintptr_t)prepared & 31) == 0), "features_prepared: prepared weights required");
+    return features_impl(img, H, W, pad, num_layers, weights_host, biases_host, (const float *)prepared, out, scratch, stream);
 }
 
 }  // extern "C"

@@ -31,7 +31,7 @@ STAGES = ("features", "cost_volume", "cbca1", "sgm", "cbca2", "wta", "interpolat
 
 class StereoMatcher(object):
 
-    def __init__(self, H, W, ndisp, checkpoint=None, stages=STAGES, cbca_mode=None, **hp):
+    def __init__(self, H, W, ndisp, checkpoint=None, stages=STAGES, cbca_mode=None, fuse_wta=True, **hp):
         torch = _pf._torch()
         self.torch = torch
         self.H, self.W, self.D = int(H), int(W), int(ndisp)
@@ -75,6 +75,10 @@ class StereoMatcher(object):
         self.d2h_bytes = H * W * 4
         self.cbca_mode = _pf.CBCA_MODE if cbca_mode is None else int(cbca_mode)
         self.cbca_modes = [_pf.CBCA_SEPARABLE if self.cbca_mode == _pf.CBCA_AUTO else self.cbca_mode] * 2
+        # winner-take-all folded into the closing column pass of the second aggregation (mccnn_cbca_wta: same map, the
+        # volumes are not read again); the exact aggregation mode has no such pass and keeps the separate k_wta
+        self.fuse_wta = bool(fuse_wta) and "cbca2" in self.stages and "wta" in self.stages and self.cbca_mode != _pf.CBCA_EXACT
+        self.wta_keys = e(H, W, dtype=torch.int64) if self.fuse_wta else None
         self.final_volume = None        # HWD left volume the last run's WTA / sub-pixel read
         self.result = None
         self._steps = self._build()
@@ -92,8 +96,8 @@ class StereoMatcher(object):
 
         def make_feature(i):
             def feature():
-                call("mccnn_features", p(img[i]), H, W, self.pad, self.pad, self.weights.w_table,
-                     self.weights.b_table, p(feat[i]), p(self.feat_scratch), sp())
+                call("mccnn_features_prepared", p(img[i]), H, W, self.pad, self.pad, self.weights.w_table,
+                     self.weights.b_table, p(self.weights.prepared), p(feat[i]), p(self.feat_scratch), sp())
             return feature
 
         self._feature_fns = [make_feature(0), make_feature(1)]
@@ -125,6 +129,13 @@ class StereoMatcher(object):
                     call("mccnn_cbca", p(src[i]), p(dst[i]), p(self.volS), p(self.arms[i]), p(self.count[i]), D, H, W,
                          iters, int(hp["cbca_distance"]), int(self.cbca_modes[i]), sp())
             return cbca
+
+        def make_cbca_wta(src, dst, iters, disp):
+            def cbca_wta():
+                for i in range(2):
+                    call("mccnn_cbca_wta", p(src[i]), p(dst[i]), p(self.volS), p(self.arms[i]), p(self.count[i]), D, H, W,
+                         iters, int(hp["cbca_distance"]), int(self.cbca_modes[i]), 1, p(self.wta_keys), p(disp[i]), sp())
+            return cbca_wta
 
         def make_sgm(vol):
             def sgm():
@@ -177,12 +188,16 @@ class StereoMatcher(object):
             steps.append(("sgm", make_sgm(cur)))
         if "cbca2" in st:
             dst = self.volA if cur is self.volB else self.volB
-            steps.append(("cbca2", make_cbca(cur, dst, int(hp["cbca_num_iterations2"]))))
+            if self.fuse_wta:
+                steps.append(("cbca2", make_cbca_wta(cur, dst, int(hp["cbca_num_iterations2"]), self.disp)))
+            else:
+                steps.append(("cbca2", make_cbca(cur, dst, int(hp["cbca_num_iterations2"]))))
             cur = dst
         self.final_volume = cur
         d = None
         if "wta" in st:
-            steps.append(("wta", make_wta(cur, self.disp)))
+            if not self.fuse_wta:
+                steps.append(("wta", make_wta(cur, self.disp)))
             d = self.disp[0]
         if "interpolation" in st:
             steps.append(("interpolation", make_interp(d, self.disp[1], self.tmp[0])))

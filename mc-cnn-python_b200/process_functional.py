@@ -178,6 +178,11 @@ class DeviceWeights(object):
         n = self.num_layers
         self.w_table = (ctypes.c_void_p * n)(*[w.data_ptr() for w in self.w])
         self.b_table = (ctypes.c_void_p * n)(*[b.data_ptr() for b in self.b])
+        # the constant part of the network, once: hi/lo tf32 split of the weights of layers 2..n (mccnn_features_prepare)
+        nb = int(_ffi.lib().mccnn_features_weights_bytes(n))
+        self.prepared = _torch().empty((max(nb, 32) + 3) // 4, dtype=_torch().float32, device=self.w[0].device)
+        _ffi.call("mccnn_features_prepare", n, self.w_table, _ffi.ptr(self.prepared), _ffi.stream_ptr())
+        _torch().cuda.current_stream().synchronize()        # (used from whichever stream calls the network later)
 
 
 def resolve_weights(checkpoint, num_layers=5):
@@ -210,8 +215,8 @@ def net_forward(image2d, dw, pad, out=None, scratch=None):
     nbytes = int(_ffi.lib().mccnn_features_scratch_bytes(H, W, pad, n))
     if scratch is None or scratch.numel() * scratch.element_size() < nbytes:
         scratch = torch.empty((max(nbytes, 4) + 3) // 4, dtype=torch.float32, device=image2d.device)
-    _ffi.call("mccnn_features", _ffi.ptr(image2d), H, W, pad, n, dw.w_table, dw.b_table, _ffi.ptr(out),
-              _ffi.ptr(scratch), _ffi.stream_ptr())
+    _ffi.call("mccnn_features_prepared", _ffi.ptr(image2d), H, W, pad, n, dw.w_table, dw.b_table, _ffi.ptr(dw.prepared),
+              _ffi.ptr(out), _ffi.ptr(scratch), _ffi.stream_ptr())
     return out
 
 

@@ -287,9 +287,9 @@ class SlabRank(object):
         p, call, sp, pl = _ffi.ptr, _ffi.call, _ffi.stream_ptr, self.plan
         a, b = max(0, self.h0 - self.pad), min(pl.H, self.h1 + self.pad)
         for i in range(2):
-            call("mccnn_features", ctypes.c_void_p(self.img[i].data_ptr() + 4 * a * pl.W), b - a, pl.W, self.pad, self.pad,
-                 self.weights.w_table, self.weights.b_table, ctypes.c_void_p(self.feat[i].data_ptr() + 4 * a * pl.W * 64),
-                 p(self.feat_scratch), sp())
+            call("mccnn_features_prepared", ctypes.c_void_p(self.img[i].data_ptr() + 4 * a * pl.W), b - a, pl.W, self.pad, self.pad,
+                 self.weights.w_table, self.weights.b_table, p(self.weights.prepared),
+                 ctypes.c_void_p(self.feat[i].data_ptr() + 4 * a * pl.W * 64), p(self.feat_scratch), sp())
 
     def send_features(self, i):
         return [self.feat[i][self.h0:self.h1] for _ in range(self.plan.world)]

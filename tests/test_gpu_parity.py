@@ -92,6 +92,21 @@ def test_features_with_the_shipped_checkpoint(pf, oracle, features_golden, check
     np.testing.assert_allclose(fb, oracle.net_forward(big, ws, bs), atol=FEAT_ATOL, rtol=0)
 
 
+def test_features_with_prepared_weights_are_the_bits_of_the_plain_call(pf):
+    """mccnn_features_prepared (weights split once per network, what the Python surface uses) == mccnn_features."""
+    import torch
+    ffi = pf._ffi
+    H, W, pad = 37, 150, 5
+    img = torch.randn((H, W), device="cuda")
+    dw = pf.resolve_weights(None, num_layers=5)
+    a = pf.net_forward(img, dw, pad)
+    b = torch.empty_like(a)
+    nb = int(ffi.lib().mccnn_features_scratch_bytes(H, W, pad, 5))
+    scratch = torch.empty((nb + 3) // 4, dtype=torch.float32, device="cuda")
+    ffi.call("mccnn_features", ffi.ptr(img), H, W, pad, 5, dw.w_table, dw.b_table, ffi.ptr(b), ffi.ptr(scratch), ffi.stream_ptr())
+    assert torch.equal(a, b)
+
+
 def test_features_of_a_row_band_are_the_bits_of_the_whole_image(pf):
     """The net is local (11x11 receptive field), so rows [lo, hi) of the features need image rows [lo-5, hi+5) only --
     what the row-band feature exchange of the slab partition relies on.  The tensor-core layers must also give the SAME
@@ -435,6 +450,36 @@ def test_wta_first_minimum_rule(pf, D, H, W):
     dl, dr = pf.disparity_prediction(vol, -vol)
     assert eq(dl, np.argmin(vol, axis=0).astype(np.float32))
     assert eq(dr, np.argmin(-vol, axis=0).astype(np.float32))
+
+
+@pytest.mark.parametrize("D,H,W,levels,iters", [(2, 9, 21, 4, 1), (11, 13, 40, 6, 2), (70, 24, 75, 4, 3), (192, 20, 130, 3, 2), (400, 6, 45, 3, 2)])
+def test_wta_folded_into_the_aggregation_is_the_separate_wta(pf, D, H, W, levels, iters):
+    """mccnn_cbca_wta (the closing column pass of the aggregation takes the first minimum itself) returns the volume of
+    mccnn_cbca and the map mccnn_wta makes of it, bit for bit: ties (quantised costs), -0.0 / +0.0, +inf and NaN cells,
+    both separable schedules, with and without storing the volume."""
+    import torch
+    ffi = pf._ffi
+    rng = np.random.default_rng(D + H)
+    li, _ = synth_images(D, H, W, levels, 2)
+    arms, count = pf.cross_arms(li, 0.02, 14)
+    vol = (rng.integers(0, 5, (H, W, ffi.dpitch(D))) * 0.25).astype(np.float32)   # sums of quarters are exact: ties survive
+    vol[rng.random(vol.shape) < 0.02] *= -0.0                                     # signed zeros among the ties
+    vol[0, 0, :] = np.inf                                                         # a pixel with no finite cost at all
+    vol[H - 1, W - 1, : max(1, D // 2)] = np.nan
+    hwd = torch.from_numpy(vol).cuda()
+    keys = torch.empty((H, W), dtype=torch.int64, device="cuda")
+    for mode in (pf.CBCA_SEPARABLE, pf.CBCA_SEPARABLE_TWO_PASS):
+        ref = pf._cbca_one(hwd, D, arms, count, iters, 14, mode=mode)
+        want = pf._wta(ref, D)
+        for store in (1, 0):
+            out, scr = torch.empty_like(hwd), torch.empty_like(hwd)
+            disp = torch.empty((H, W), dtype=torch.float32, device="cuda")
+            ffi.call("mccnn_cbca_wta", ffi.ptr(hwd), ffi.ptr(out), ffi.ptr(scr), ffi.ptr(arms), ffi.ptr(count), D, H, W, iters, 14,
+                     mode, store, ffi.ptr(keys), ffi.ptr(disp), ffi.stream_ptr())
+            assert torch.equal(disp, want), (mode, store, int((disp != want).sum()))
+            if store:
+                assert eq(out[:, :, :D].cpu().numpy(), ref[:, :, :D].cpu().numpy())
+    assert float(want[0, 0]) == -1.0
 
 
 def test_wta_full_size_config2(pf):
