@@ -7,7 +7,6 @@
 // HWD layout makes that walk cheap: the lanes of a warp are the disparities of one or two
 // pixels, so every lane follows the same arms (no divergence) and every load is a contiguous
 // 16 B granule of the neighbour pixel's disparity row (fully coalesced for any region shape).
-#include <stdlib.h>
 #include "common.cuh"
 #include "cbca_stream.cuh"
 #include "cbca_chain.cuh"
@@ -154,51 +153,56 @@ static int two_pass_rounds(const float *in, float *out, float *scratch, const Cs
     return MCCNN_OK;
 }
 
+// The chained round's shapes (cbca_chain.cuh): pixels per segment, threads, resident CTAs asked for, granules per thread.
+// Measured at 1024 x 1024, natural image, ms per round of a 16-round call (B200):
+//   ndisp 192 (48 granules): G1 0.386, G3 0.364 (other GPT = 3 shapes: 30 px x 128 thr 0.411, 30 x 256 0.370, 22 x 192 0.366,
+//                            14 x 256 0.479, 14 x 64 0.415); round 2's cp.async kernel 0.438, two streaming passes 0.580
+//   ndisp 256 (64 granules): G1 0.508, G2 0.481 (30 px x 256 thr 0.490), four granules per thread 0.522
+//   ndisp 400 (100 granules): G1 0.894, G2 0.985, G3 1.170 (granule groups are padded to 16 x GPT: dead lanes)
+typedef CgShape<30, 128, 8, 1> CgG1;         // 25 KB, 8 CTAs per SM
+typedef CgShape<14, 128, 8, 2> CgG2;         // 25 KB
+typedef CgShape<14, 128, 6, 3> CgG3;         // 37 KB, 6 CTAs per SM
+
 template <class C>
-static int launch_colrow_shape(const float *hs_in, float *hs_out, const uint8_t *arms, const int32_t *count, int G, int H, int W,
-                               cudaStream_t s) {
+static int launch_colrow_g(const float *hs_in, float *hs_out, const uint8_t *arms, const int32_t *count, int G, int H, int W,
+                           cudaStream_t s) {
+    CUtensorMap map;
+    int rc = tc_encode_map_3d(map, hs_in, (unsigned long long)G * 4, W, H, CS_GC * 4 * C::GPT, C::NP, false, "cbca", 3);
+    if (rc) return rc;
     // per device and cheap: set on every launch rather than cached in a process-wide static
-    MCCNN_CUDA(cudaFuncSetAttribute(k_cbca_colrow<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
-    dim3 grid(cdiv(G, CS_GC), cdiv(W, C::S), H);
-    k_cbca_colrow<C><<<grid, C::NT, C::SMEM, s>>>(reinterpret_cast<const float4 *>(hs_in), reinterpret_cast<float4 *>(hs_out),
-                                                  reinterpret_cast<const uchar4 *>(arms), count, G, H, W);
+    MCCNN_CUDA(cudaFuncSetAttribute(k_cbca_colrow_g<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
+    dim3 grid(cdiv(G, CS_GC * C::GPT), cdiv(W, C::S), H);
+    k_cbca_colrow_g<C><<<grid, C::NT, C::SMEM, s>>>(map, reinterpret_cast<const float4 *>(hs_in), reinterpret_cast<float4 *>(hs_out),
+                                                    reinterpret_cast<const uchar4 *>(arms), count, G, H, W);
     MCCNN_LAUNCHED("cbca_colrow");
     return MCCNN_OK;
 }
 
-template <class C>
-static int launch_colrow_tma_shape(const CUtensorMap &map, const float *hs_in, float *hs_out, const uint8_t *arms, const int32_t *count,
-                                   int G, int H, int W, cudaStream_t s) {
-    MCCNN_CUDA(cudaFuncSetAttribute(k_cbca_colrow_tma<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
-    dim3 grid(cdiv(G, CS_GC), cdiv(W, C::S), H);
-    k_cbca_colrow_tma<C><<<grid, C::NT, C::SMEM, s>>>(map, reinterpret_cast<const float4 *>(hs_in), reinterpret_cast<float4 *>(hs_out),
-                                                      reinterpret_cast<const uchar4 *>(arms), count, G, H, W);
-    MCCNN_LAUNCHED("cbca_colrow_tma");
-    return MCCNN_OK;
+// granules per thread for a pitch of G granules: the cheapest padded cover, cost per 16 granules 1 / 0.947 / 0.943 for
+// GPT = 1 / 2 / 3 from the table above; 0 if no shape holds the far halo of arms up to hm pixels (two passes then)
+static int colrow_gpt(int G, int hm) {
+    const double c[4] = {0.0, 1.0, 0.947, 0.943};
+    const bool ok[4] = {false, CgG1::supports(hm), CgG2::supports(hm), CgG3::supports(hm)};
+    int best = 0;
+    double bc = 1e30;
+    for (int gpt = 1; gpt <= 3; gpt++) {
+        const double cost = cdiv(G, CS_GC * gpt) * gpt * c[gpt];
+        if (ok[gpt] && cost < bc) { bc = cost; best = gpt; }
+    }
+    return best;
 }
 
-// experiment switch (read once): MCCNN_CBCA_CHAIN = 0 cp.async narrow (r2 default), 1 TMA narrow, 2 TMA wide, 3 cp.async wide
-static int chain_variant() {
-    static int v = -1;
-    if (v < 0) { const char *e = getenv("MCCNN_CBCA_CHAIN"); v = e ? atoi(e) : 1; }
-    return v;
-}
-
-// Measured at C3, ms per round of a 16-round call (natural / piece-wise constant image): CcNarrow 0.438 / 2.65,
-// CcWide 0.448 / 2.38, CcNarrow with two staged halo pixels per side 0.451 / 2.78, two streaming passes 0.580 / 1.85.
-static int launch_colrow(const CUtensorMap *map, const float *hs_in, float *hs_out, const uint8_t *arms, const int32_t *count, int G,
-                         int H, int W, cudaStream_t s) {
-    const int v = chain_variant();
-    if (map && v == 1) return launch_colrow_tma_shape<CcNarrow>(*map, hs_in, hs_out, arms, count, G, H, W, s);
-    if (map && v == 2) return launch_colrow_tma_shape<CcWide>(*map, hs_in, hs_out, arms, count, G, H, W, s);
-    if (v == 3) return launch_colrow_shape<CcWide>(hs_in, hs_out, arms, count, G, H, W, s);
-    return launch_colrow_shape<CcNarrow>(hs_in, hs_out, arms, count, G, H, W, s);
+static int launch_colrow(int gpt, const float *hs_in, float *hs_out, const uint8_t *arms, const int32_t *count, int G, int H, int W,
+                         cudaStream_t s) {
+    if (gpt == 3) return launch_colrow_g<CgG3>(hs_in, hs_out, arms, count, G, H, W, s);
+    if (gpt == 2) return launch_colrow_g<CgG2>(hs_in, hs_out, arms, count, G, H, W, s);
+    return launch_colrow_g<CgG1>(hs_in, hs_out, arms, count, G, H, W, s);
 }
 
 // n >= 2 rounds, chained: rows | (n-1) x colrow | cols.  The row sums ping-pong between `out` and `scratch` so that
 // the last ones sit in `scratch` and the closing column pass can write `out` (or scatter, sc != NULL).
 static int chained_rounds(const float *in, float *out, float *scratch, const CsScatter *sc, const CsWta *wt, const uint8_t *arms,
-                          const int32_t *count, int G, int H, int W, int iters, cudaStream_t s) {
+                          const int32_t *count, int G, int H, int W, int iters, int gpt, cudaStream_t s) {
     dim3 grid(cdiv(G, CS_GC), cdiv(W, CS_PW), cdiv(H, CS_PH));
     float *hs[2];
     hs[(iters - 1) & 1] = scratch;
@@ -206,18 +210,8 @@ static int chained_rounds(const float *in, float *out, float *scratch, const CsS
     k_cbca_pass<false, CS_ITEMS, 1><<<grid, CS_THREADS, 0, s>>>(reinterpret_cast<const float4 *>(in), reinterpret_cast<float4 *>(hs[0]),
                                                                 reinterpret_cast<const uchar4 *>(arms), count, G, H, W);
     MCCNN_LAUNCHED("cbca_rows");
-    // tensor maps of the two row-sum buffers for the TMA load of k_cbca_colrow_tma: {Dp, W, H}, box {64, NP, 3}
-    CUtensorMap maps[2];
-    const int v = chain_variant();
-    const bool use_tma = v == 1 || v == 2;
-    if (use_tma)
-        for (int b = 0; b < 2 && b < iters - 1; b++) {
-            int rc = tc_encode_map_3d(maps[b], hs[b], (unsigned long long)G * 4, W, H, CS_GC * 4, v == 2 ? CcWide::NP : CcNarrow::NP,
-                                      false, "cbca", 3);
-            if (rc) return rc;
-        }
     for (int k = 1; k < iters; k++) {
-        int rc = launch_colrow(use_tma ? &maps[(k - 1) & 1] : nullptr, hs[(k - 1) & 1], hs[k & 1], arms, count, G, H, W, s);
+        int rc = launch_colrow(gpt, hs[(k - 1) & 1], hs[k & 1], arms, count, G, H, W, s);
         if (rc) return rc;
     }
     return closing_cols(scratch, out, sc, wt, arms, count, G, H, W, s);
@@ -226,7 +220,8 @@ static int chained_rounds(const float *in, float *out, float *scratch, const CsS
 // the default: chained rounds wherever they apply (two rounds or more; the shared-memory tile grows with the arm limit)
 static int separable_rounds(const float *in, float *out, float *scratch, const CsScatter *sc, const CsWta *wt, const uint8_t *arms,
                             const int32_t *count, int G, int H, int W, int iters, int hm, cudaStream_t s) {
-    if (iters >= 2 && CcNarrow::supports(hm)) return chained_rounds(in, out, scratch, sc, wt, arms, count, G, H, W, iters, s);
+    const int gpt = colrow_gpt(G, hm);
+    if (iters >= 2 && gpt) return chained_rounds(in, out, scratch, sc, wt, arms, count, G, H, W, iters, gpt, s);
     return two_pass_rounds(in, out, scratch, sc, wt, arms, count, G, H, W, iters, s);
 }
 
