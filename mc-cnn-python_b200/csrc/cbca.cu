@@ -155,25 +155,30 @@ static int two_pass_rounds(const float *in, float *out, float *scratch, const Cs
 
 // The chained round's shapes (cbca_chain.cuh): pixels per segment, threads, resident CTAs asked for, granules per thread.
 // Measured at 1024 x 1024, natural image, ms per round of a 16-round call (B200):
-//   ndisp 192 (48 granules): G1 0.386, G3 0.364 (other GPT = 3 shapes: 30 px x 128 thr 0.411, 30 x 256 0.370, 22 x 192 0.366,
-//                            14 x 256 0.479, 14 x 64 0.415); round 2's cp.async kernel 0.438, two streaming passes 0.580
-//   ndisp 256 (64 granules): G1 0.508, G2 0.481 (30 px x 256 thr 0.490), four granules per thread 0.522
-//   ndisp 400 (100 granules): G1 0.894, G2 0.985, G3 1.170 (granule groups are padded to 16 x GPT: dead lanes)
+//   ndisp 192 (48 granules): G1 0.362, G3 0.333 (other GPT = 3 shapes: 14 px x 128 thr 0.334, 30 x 256 0.338, 22 x 128 0.356,
+//                            30 x 128 0.383; without the L2 look-ahead G3 is 0.364); round 2's first cp.async kernel 0.438,
+//                            two streaming passes 0.580
+//   ndisp 256 (64 granules): G2 0.449 (before the look-ahead: G1 0.508, G2 0.481, four granules per thread 0.522)
+//   ndisp 400 (100 granules): G1 0.826 (before the look-ahead: G1 0.894, G2 0.985, G3 1.170; granule groups are padded to
+//                            16 x GPT: dead lanes)
 typedef CgShape<30, 128, 8, 1> CgG1;         // 25 KB, 8 CTAs per SM
 typedef CgShape<14, 128, 8, 2> CgG2;         // 25 KB
-typedef CgShape<14, 128, 6, 3> CgG3;         // 37 KB, 6 CTAs per SM
+typedef CgShape<22, 192, 4, 3> CgG3;         // 55 KB, 4 CTAs of 6 warps per SM
 
 template <class C>
 static int launch_colrow_g(const float *hs_in, float *hs_out, const uint8_t *arms, const int32_t *count, int G, int H, int W,
                            cudaStream_t s) {
-    CUtensorMap map;
+    CUtensorMap map, map_row;
     int rc = tc_encode_map_3d(map, hs_in, (unsigned long long)G * 4, W, H, CS_GC * 4 * C::GPT, C::NP, false, "cbca", 3);
     if (rc) return rc;
+    rc = tc_encode_map_3d(map_row, hs_in, (unsigned long long)G * 4, W, H, CS_GC * 4 * C::GPT, C::NP, false, "cbca", 1);
+    if (rc) return rc;
+    const int ahead = 8;      // rows of L2 look-ahead; measured at C3: 0 -> 0.362 ms per round, 4 .. 24 -> 0.339, 32 -> 0.350, 64 -> 0.384
     // per device and cheap: set on every launch rather than cached in a process-wide static
     MCCNN_CUDA(cudaFuncSetAttribute(k_cbca_colrow_g<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
     dim3 grid(cdiv(G, CS_GC * C::GPT), cdiv(W, C::S), H);
-    k_cbca_colrow_g<C><<<grid, C::NT, C::SMEM, s>>>(map, reinterpret_cast<const float4 *>(hs_in), reinterpret_cast<float4 *>(hs_out),
-                                                    reinterpret_cast<const uchar4 *>(arms), count, G, H, W);
+    k_cbca_colrow_g<C><<<grid, C::NT, C::SMEM, s>>>(map, map_row, reinterpret_cast<const float4 *>(hs_in), reinterpret_cast<float4 *>(hs_out),
+                                                    reinterpret_cast<const uchar4 *>(arms), count, G, H, W, ahead);
     MCCNN_LAUNCHED("cbca_colrow");
     return MCCNN_OK;
 }

@@ -115,10 +115,13 @@ __device__ __forceinline__ void cg_walk(float4 (&acc)[GPT], const float4 *__rest
 }
 
 template <class C>
-__global__ void __launch_bounds__(C::NT, C::MINB) k_cbca_colrow_g(const __grid_constant__ CUtensorMap map, const float4 *__restrict__ src,
+__global__ void __launch_bounds__(C::NT, C::MINB) k_cbca_colrow_g(const __grid_constant__ CUtensorMap map,
+                                                                  const __grid_constant__ CUtensorMap map_row,
+                                                                  const float4 *__restrict__ src,
                                                                   float4 *__restrict__ dst, const uchar4 *__restrict__ arms,
-                                                                  const int32_t *__restrict__ count, int G, int H, int W) {
+                                                                  const int32_t *__restrict__ count, int G, int H, int W, int ahead) {
     constexpr int S = C::S, NP = C::NP, HL = C::HL, GPT = C::GPT, PB = C::PB, SLOTS = C::SLOTS;
+    static_assert(NP <= 32 && NP % SLOTS == 0 && C::NT >= 64, "one warp makes the per-pixel information; whole sweeps of the pixel slots");
     extern __shared__ __align__(128) unsigned char cc_raw[];
     __shared__ int reach[2];
     __shared__ __align__(8) unsigned long long bar;
@@ -132,6 +135,14 @@ __global__ void __launch_bounds__(C::NT, C::MINB) k_cbca_colrow_g(const __grid_c
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
         tc_mbar_expect_tx(&bar, 3 * NP * PB);
         tc_tma_load_3d(cc_raw, &map, blockIdx.x * (CS_GC * GPT * 4), w0 - HL, h - 1, &bar);
+        // Rows h-1 and h were fetched by the CTAs of the rows above (L2 hits); row h+1 is first touched here, so the box
+        // would wait for DRAM.  Ask L2 for the row that the CTA `ahead` rows below will be the first to touch: by the
+        // time it runs, all three of its rows are L2 hits (map_row: the same tensor, box of one row).
+        if (ahead > 0 && h + 1 + ahead < H)
+            asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];\n" ::"l"(
+                             reinterpret_cast<unsigned long long>(&map_row)),
+                         "r"((int)(blockIdx.x * (CS_GC * GPT * 4))), "r"(w0 - HL), "r"(h + 1 + ahead)
+                         : "memory");
         reach[0] = 0; reach[1] = 0;
     }
     unsigned jm = 0;                                                  // this thread's granules that exist
@@ -145,7 +156,8 @@ __global__ void __launch_bounds__(C::NT, C::MINB) k_cbca_colrow_g(const __grid_c
     const float4 *cbase = src + (rowp + w0 - HL) * G + g;              // staged pixel 0, this lane's first granule
     const unsigned my = gi * 16;
     int lneed, rneed;
-    const bool far = cc_pixel_info<C>(arms, count, rowp, w0, tid, p_lo, np, sv, sP, lneed, rneed);
+    // (the last warp, so that its loads are not queued behind thread 0's TMA set-up)
+    const bool far = cc_pixel_info<C>(arms, count, rowp, w0, tid - (C::NT - 32), p_lo, np, sv, sP, lneed, rneed);
     const int any_far = __syncthreads_or(far);                        // publishes the per-pixel information and the mbarrier
     tc_mbar_wait(&bar, 0);
 
