@@ -513,8 +513,8 @@ def run_ours(args):
         cells_rank = cells / world if slab else cells           # a rank's slab of every volume
         # algorithmic bytes per stage and launches of the stage's main kernel
         # ("launch" of a CBCA round = one round on one volume: a call of n rounds is  k_cbca_pass<rows> | (n-1) x
-        #  k_cbca_colrow | k_cbca_pass<cols>, n + 1 kernels that each move 8 B/cell; the algorithmic figure is 8 B/cell/round)
-        cbca_kernels = "k_cbca_colrow (+ k_cbca_pass<rows> / <cols> at the ends of a call)"
+        #  k_cbca_colrow_g | k_cbca_pass<cols>, n + 1 kernels that each move 8 B/cell; the algorithmic figure is 8 B/cell/round)
+        cbca_kernels = "k_cbca_colrow_g (+ k_cbca_pass<rows> / <cols> at the ends of a call; the closing <cols> of the second aggregation also takes the WTA minimum)"
         model = {
             "cbca2": (8.0 * cells_rank * it2 * 2, it2 * 2, cbca_kernels),
         } if slab else {

@@ -92,7 +92,7 @@ int mccnn_cross_region_list(const uint8_t *arms, int32_t *region, int H, int W,
  * more HWD volume.
  * mode MCCNN_CBCA_SEPARABLE (default): row sums re-used down each column (<= 54 additions per cell at
  *      distance_threshold 14); equals the reference up to float32 re-association of the sum (~1e-7 relative).
- *      The rounds of a call are chained: one row pass, then per further round ONE kernel (k_cbca_colrow) that forms a
+ *      The rounds of a call are chained: one row pass, then per further round ONE kernel (k_cbca_colrow_g) that forms a
  *      round's column sums + division in shared memory and the next round's row sums from them, then one column pass:
  *      8 instead of 16 B per cell per round through HBM.  `scratch` is needed for any iters >= 1.
  * mode MCCNN_CBCA_SEPARABLE_TWO_PASS: the same sums in the same order as two streaming passes per round (rows into

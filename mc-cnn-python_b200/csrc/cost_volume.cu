@@ -7,22 +7,29 @@
 // the two volumes.  For one image row the scores are a banded slice of the GEMM
 // S = FL[h] (W x 64) . FR[h]^T (64 x W): only x = w - d with 0 <= d < ndisp is needed.
 //
-// k_cost_volume_tc: persistent, one CTA per SM, 256 threads in two groups.
-//   front end (warps 0-3): TMA (cp.async.bulk.tensor, 128B swizzle) brings the 128-pixel left tile and,
-//       128 right pixels at a time, the right rows it can match; the float32 operands are split in
-//       shared memory into hi = tf32(x) and lo = x - hi (exact), and one thread issues tcgen05.mma
-//       kind::tf32 three times per K step -- hi.hi + hi.lo + lo.hi, accumulated in float32 in TMEM --
-//       which restores float32-level accuracy (error ~1e-6 of the volume's scale; plain TF32 would
-//       break the 1e-4 gate).  Accumulators are double buffered in TMEM so the
-//       next chunk is loaded, split and multiplied while the previous one is written out.
-//       Both S (lanes = left pixels) and S^T (lanes = right pixels) are formed -- the tensor pipe is
-//       far from busy -- so that neither volume needs a transpose on the way out; the negation
-//       (pf:111-112) is the descriptor's negate-A bit.
-//   epilogue (warps 4-7, one per TMEM lane quarter): tcgen05.ld 32 columns at a time.  A column of S
-//       is one right pixel x and the 32 lanes of a warp are consecutive left pixels w, i.e.
-//       consecutive d = w - x: R[h][x][d..d+31] is one coalesced 128-byte store straight from
-//       registers; S^T gives L[h][w][d..d-31] the same way.  Column groups whose d range lies
-//       outside [0, ndisp) are skipped.
+// k_cost_volume_tc: persistent, one CTA per SM, 512 threads in two groups.
+//   front end (warps 0-7): TMA (cp.async.bulk.tensor, 128B swizzle) brings the 128-pixel left tile and, 64 right pixels
+//       at a time, the right rows it can match; the float32 operands are split in shared memory into hi = tf32(x) and
+//       lo = x - hi (exact), and one thread issues tcgen05.mma kind::tf32 three times per K step -- hi.hi + hi.lo +
+//       lo.hi, accumulated in float32 in TMEM -- which restores float32-level accuracy (error ~1e-6 of the volume's
+//       scale; plain TF32 would break the 1e-4 gate).  S (lanes = left pixels w, columns = right
+//       pixels x) sits in one of four TMEM accumulators, so the next chunks are loaded, split and multiplied while the
+//       previous ones are written out; the negation (pf:111-112) is the descriptor's negate-A bit.
+//   epilogue (warps 8-15, two per TMEM lane quarter: one writes R, one writes L, from the same accumulator).
+//       Both volumes are [pixel][d], d = w - x, so a tile's cells are parallelograms: whatever the mapping, a pixel's
+//       disparities come out of a (tile, chunk) pair as a contiguous run that starts at an arbitrary float.  B200's L2
+//       takes stores at full speed only in whole 32-byte sectors (scripts/microbench/span_write.cu: 6.3 TB/s against
+//       2.8-3.5 TB/s for 128-byte runs that start mid-sector).
+//       R: a column of S is one right pixel x and the 32 lanes of a warp are consecutive left pixels w, i.e.
+//          consecutive d = w - x: R[h][x][d..d+31] is one coalesced 128-byte store straight from tcgen05.ld registers
+//          (it starts mid-sector 7 times out of 8: the slow kind).
+//       L: a lane IS a left pixel, and all of its disparities are produced by this warp in this tile, 32 per column
+//          group, descending.  The lane scatters them into its own 64-float ring in shared memory (bank = d mod 32:
+//          conflict free); after every group exactly one aligned 32-float line per pixel is complete and the warp writes
+//          those 32 lines as whole 128-byte lines (8 lanes x float4 per line).  Every L sector is written once, whole.
+//       Round 1 formed S^T as well and wrote both volumes the R way (0.575 ms); staging R through shared memory too
+//       (scripts/experiments/cost_volume_staged.cu) makes every store a whole sector but costs eight times the
+//       instructions (0.72 ms): the epilogue becomes issue bound.  This mix measures 0.52 ms.
 // k_cost_fill then overwrites the cells that have no correspondent.
 #include "tc_common.cuh"
 
@@ -30,22 +37,39 @@ namespace mccnn {
 
 constexpr int CV_C = 64;                   // feature channels (model.py:38)
 constexpr int CV_BM = 128;                 // left pixels per tile
-constexpr int CV_BN = 128;                 // right pixels per chunk
-constexpr int CV_KB_BYTES = 128 * 128;     // one K block: 128 rows x 32 floats, 128B-swizzled
-constexpr int CV_TILE_BYTES = 2 * CV_KB_BYTES;
+constexpr int CV_BN = 64;                  // right pixels per chunk
+constexpr int CV_KA_BYTES = CV_BM * 128;   // one K block of the left tile: 128 rows x 32 floats, 128B-swizzled
+constexpr int CV_KB_BYTES = CV_BN * 128;   // one K block of a right chunk
+constexpr int CV_A_BYTES = 2 * CV_KA_BYTES, CV_B_BYTES = 2 * CV_KB_BYTES;
 constexpr int CV_THREADS = 512;            // warp 0: MMA issue, warp 1: TMA, warps 2-7: operand split, 8-11: R, 12-15: L
 constexpr int CV_NSPLIT = 192;             // splitter threads (warps 2-7)
-constexpr int CV_TMEM_COLS = 512;          // 2 buffers x (S: lanes = left pixels | S^T: lanes = right pixels)
+constexpr int CV_NACC = 4;                 // TMEM accumulators (64 columns each)
+constexpr int CV_TMEM_COLS = CV_NACC * CV_BN;
+constexpr int CV_RING = 64;                // floats per pixel in an L warp's ring (two lines)
 
 struct __align__(1024) CvSmem {
-    unsigned char a_hi[CV_TILE_BYTES], a_lo[CV_TILE_BYTES];            // left tile, split
-    unsigned char a_raw[CV_TILE_BYTES];                                // next left tile as loaded (prefetch)
-    unsigned char b_hi[2][CV_TILE_BYTES], b_lo[2][CV_TILE_BYTES];      // right chunks, split, double buffered
-    unsigned long long bar_tma_a, bar_tma_b[2], bar_full[2], bar_empty[2];
+    unsigned char a_hi[CV_A_BYTES], a_lo[CV_A_BYTES];                  // left tile, split
+    unsigned char a_raw[CV_A_BYTES];                                   // next left tile as loaded (prefetch)
+    unsigned char b_hi[2][CV_B_BYTES], b_lo[2][CV_B_BYTES];            // right chunks, split, double buffered
+    float l_ring[4][32 * CV_RING];                                     // per L warp: [pixel (lane)][d mod 64]
+    unsigned long long bar_tma_a, bar_tma_b[2], bar_full[CV_NACC], bar_empty[CV_NACC];
     unsigned tmem_base;
 };
+static_assert(sizeof(CvSmem) <= 232448, "shared memory of k_cost_volume_tc");
 
-struct CvMaps { CUtensorMap fl, fr; };      // [H][W][64] float32, box {32 channels, 128 pixels, 1 row}, SWIZZLE_128B
+struct CvMaps { CUtensorMap fl, fr; };      // [H][W][64] float32, box {32 channels, 128 | 64 pixels, 1 row}, SWIZZLE_128B
+
+__device__ __forceinline__ void cv_sts(unsigned a, unsigned v) { asm volatile("st.shared.b32 [%0], %1;\n" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ float cv_lds(unsigned a) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];\n" : "=f"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ float4 cv_lds128(unsigned a) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];\n" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+    return v;
+}
 
 // One warp writes its 32 TMEM lanes x 128 columns of an accumulator to a volume.  Column n is pixel pix0 + n;
 // lane l holds disparity d0 + dl*l + dn*n with (dl, dn) = (+1, -1) for R (lanes = left pixels) and (-1, +1)
@@ -106,19 +130,21 @@ k_cost_volume_tc(const __grid_constant__ CvMaps maps, float *__restrict__ L, flo
         tc_mbar_init(&sm.bar_tma_a, 1);
         tc_mbar_init(&sm.bar_tma_b[0], 1);
         tc_mbar_init(&sm.bar_tma_b[1], 1);
-        tc_mbar_init(&sm.bar_full[0], 1);
-        tc_mbar_init(&sm.bar_full[1], 1);
-        tc_mbar_init(&sm.bar_empty[0], 256);
-        tc_mbar_init(&sm.bar_empty[1], 256);
+        for (int i = 0; i < CV_NACC; i++) {
+            tc_mbar_init(&sm.bar_full[i], 1);
+            tc_mbar_init(&sm.bar_empty[i], 256);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
     const unsigned tmem_base = sm.tmem_base;
-    // instruction descriptor: D = F32, A = B = TF32, A negated (pf:111-112), both K-major, N = 128, M = 128
+    // instruction descriptor: D = F32, A = B = TF32, A negated (pf:111-112), both K-major, N = 64, M = 128
     const unsigned idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 13) | ((unsigned)(CV_BN >> 3) << 17) |
                            ((unsigned)(CV_BM >> 4) << 24);
+    // chunk g of this CTA uses right-chunk stage g & 1 and accumulator g % CV_NACC; bar_full[g % CV_NACC] completes its
+    // phase (g / CV_NACC) & 1 when the MMAs of chunk g are done (they have then also finished reading the stage)
 
     if (warp == 1) {
         // ================= TMA producer (one lane) =================
@@ -127,15 +153,15 @@ k_cost_volume_tc(const __grid_constant__ CvMaps maps, float *__restrict__ L, flo
                 const int h = tile / nwt, w0 = (tile - h * nwt) * CV_BM;
                 const int x0c = w0 + CV_BM - CV_BN * nchunks + CV_BN * c;
                 unsigned char *dst = sm.b_hi[g & 1];
-                tc_mbar_expect_tx(&sm.bar_tma_b[g & 1], CV_TILE_BYTES);
+                tc_mbar_expect_tx(&sm.bar_tma_b[g & 1], CV_B_BYTES);
                 tc_tma_load_3d(dst, &maps.fr, 0, x0c - dbase, h, &sm.bar_tma_b[g & 1]);
                 tc_tma_load_3d(dst + CV_KB_BYTES, &maps.fr, 32, x0c - dbase, h, &sm.bar_tma_b[g & 1]);
             };
             auto issue_a = [&](int tile) {
                 const int h = tile / nwt, w0 = (tile - h * nwt) * CV_BM;
-                tc_mbar_expect_tx(&sm.bar_tma_a, CV_TILE_BYTES);
+                tc_mbar_expect_tx(&sm.bar_tma_a, CV_A_BYTES);
                 tc_tma_load_3d(sm.a_raw, &maps.fl, 0, w0, h, &sm.bar_tma_a);
-                tc_tma_load_3d(sm.a_raw + CV_KB_BYTES, &maps.fl, 32, w0, h, &sm.bar_tma_a);
+                tc_tma_load_3d(sm.a_raw + CV_KA_BYTES, &maps.fl, 32, w0, h, &sm.bar_tma_a);
             };
             unsigned g = 0;
             if ((int)blockIdx.x < ntiles) {
@@ -144,9 +170,9 @@ k_cost_volume_tc(const __grid_constant__ CvMaps maps, float *__restrict__ L, flo
             }
             for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
                 for (int c = 0; c < nchunks; c++, g++) {
-                    // chunk g+1 lands in the buffer chunk g-1 used: wait until the MMAs of g-1 are done with it.
+                    // chunk g+1 lands in the stage chunk g-1 used: wait until the MMAs of g-1 are done with it.
                     if (g > 0) {
-                        tc_mbar_wait_sleep(&sm.bar_full[(g - 1) & 1], ((g - 1) >> 1) & 1);
+                        tc_mbar_wait_sleep(&sm.bar_full[(g - 1) % CV_NACC], ((g - 1) / CV_NACC) & 1);
                         asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
                         // chunk g-1 opened a tile <=> c == 1 (or nchunks == 1): its split has consumed a_raw
                         const bool opened = (nchunks == 1) ? true : (c == 1);
@@ -163,68 +189,96 @@ k_cost_volume_tc(const __grid_constant__ CvMaps maps, float *__restrict__ L, flo
         unsigned g = 0, ta = 0;
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ta++) {
             for (int c = 0; c < nchunks; c++, g++) {
-                const unsigned buf = g & 1;
+                const unsigned stage = g & 1, acc_i = g % CV_NACC;
                 if (warp >= 2) {
                     if (c == 0) {
                         // the previous tile's MMAs no longer read a_hi / a_lo; the new tile was prefetched into a_raw
-                        if (g > 0) tc_mbar_wait(&sm.bar_full[(g - 1) & 1], ((g - 1) >> 1) & 1);
+                        if (g > 0) tc_mbar_wait(&sm.bar_full[(g - 1) % CV_NACC], ((g - 1) / CV_NACC) & 1);
                         tc_mbar_wait(&sm.bar_tma_a, ta & 1);
-                        tc_split(sm.a_raw, sm.a_hi, sm.a_lo, CV_TILE_BYTES, tid - 64, CV_NSPLIT);
+                        tc_split(sm.a_raw, sm.a_hi, sm.a_lo, CV_A_BYTES, tid - 64, CV_NSPLIT);
                     }
-                    tc_mbar_wait(&sm.bar_tma_b[buf], (g >> 1) & 1);
-                    tc_split(sm.b_hi[buf], sm.b_hi[buf], sm.b_lo[buf], CV_TILE_BYTES, tid - 64, CV_NSPLIT);
+                    tc_mbar_wait(&sm.bar_tma_b[stage], (g >> 1) & 1);
+                    tc_split(sm.b_hi[stage], sm.b_hi[stage], sm.b_lo[stage], CV_B_BYTES, tid - 64, CV_NSPLIT);
                     asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");   // operand accesses -> async proxy
                 }
                 tc_named_barrier(1, 32 + CV_NSPLIT);
                 if (tid == 0) {
-                    if (g >= 2) tc_mbar_wait(&sm.bar_empty[buf], ((g >> 1) - 1) & 1);   // accumulators drained by the epilogue
+                    if (g >= CV_NACC) tc_mbar_wait(&sm.bar_empty[acc_i], ((g / CV_NACC) - 1) & 1);   // drained by the epilogue
                     asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-                    const unsigned d_s = tmem_base + buf * (2 * CV_BN), d_t = d_s + CV_BN;
+                    const unsigned d_s = tmem_base + acc_i * CV_BN;
                     const unsigned long long ah = tc_smem_desc(tc_smem_u32(sm.a_hi)), al = tc_smem_desc(tc_smem_u32(sm.a_lo));
-                    const unsigned long long bh = tc_smem_desc(tc_smem_u32(sm.b_hi[buf])), bl = tc_smem_desc(tc_smem_u32(sm.b_lo[buf]));
+                    const unsigned long long bh = tc_smem_desc(tc_smem_u32(sm.b_hi[stage])), bl = tc_smem_desc(tc_smem_u32(sm.b_lo[stage]));
                     unsigned acc = 0;
 #pragma unroll
                     for (int kb = 0; kb < 2; kb++)
 #pragma unroll
                         for (int ks = 0; ks < 4; ks++) {
-                            const unsigned long long off = (unsigned long long)((kb * CV_KB_BYTES + ks * 32) >> 4);
-                            // S = -FL.FR^T (lanes = left pixels) and S^T (lanes = right pixels), each hi.hi + hi.lo + lo.hi
-                            tc_mma_tf32(d_s, ah + off, bh + off, idesc, acc);
-                            tc_mma_tf32(d_t, bh + off, ah + off, idesc, acc);
+                            const unsigned long long oa = (unsigned long long)((kb * CV_KA_BYTES + ks * 32) >> 4);
+                            const unsigned long long ob = (unsigned long long)((kb * CV_KB_BYTES + ks * 32) >> 4);
+                            // S = -FL.FR^T as hi.hi + hi.lo + lo.hi
+                            tc_mma_tf32(d_s, ah + oa, bh + ob, idesc, acc);
                             acc = 1;
-                            tc_mma_tf32(d_s, ah + off, bl + off, idesc, 1);
-                            tc_mma_tf32(d_t, bh + off, al + off, idesc, 1);
-                            tc_mma_tf32(d_s, al + off, bh + off, idesc, 1);
-                            tc_mma_tf32(d_t, bl + off, ah + off, idesc, 1);
+                            tc_mma_tf32(d_s, ah + oa, bl + ob, idesc, 1);
+                            tc_mma_tf32(d_s, al + oa, bh + ob, idesc, 1);
                         }
-                    tc_mma_commit(&sm.bar_full[buf]);
+                    tc_mma_commit(&sm.bar_full[acc_i]);
                 }
             }
         }
     } else {
-        // ================= epilogue: TMEM -> R and L, one warp per TMEM lane quarter =================
-        const int q = warp & 3;                       // TMEM lane quarter this warp may read
-        const bool does_l = warp >= 12;               // warps 8-11 write R from S, warps 12-15 write L from S^T
+        // ================= epilogue: R straight from registers, L through the per-lane rings =================
+        const int q = warp & 3;                       // TMEM lane quarter this warp may read: left pixels w0 + 32q + lane
+        const bool does_l = warp >= 12;               // warps 8-11 write R, warps 12-15 write L
+        const unsigned ring = tc_smem_u32(sm.l_ring[q]) + lane * (CV_RING * 4);      // this lane's (= left pixel's) ring
+        const int sub = lane >> 3, l8 = lane & 7;     // flush of L: 4 pixels per instruction, 8 float4 pieces per pixel
         unsigned g = 0;
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
             const int h = tile / nwt, w0 = (tile - h * nwt) * CV_BM;
             const int x_lo = w0 + CV_BM - CV_BN * nchunks;
             const size_t rowbase = (size_t)h * W;
             for (int c = 0; c < nchunks; c++, g++) {
-                const unsigned buf = g & 1;
+                const unsigned acc_i = g % CV_NACC;
                 const int x0c = x_lo + CV_BN * c;
-                tc_mbar_wait(&sm.bar_full[buf], (g >> 1) & 1);
+                tc_mbar_wait(&sm.bar_full[acc_i], (g / CV_NACC) & 1);
                 asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-                const unsigned t_s = tmem_base + ((unsigned)(32 * q) << 16) + buf * (2 * CV_BN), t_t = t_s + CV_BN;
+                const unsigned taddr = tmem_base + ((unsigned)(32 * q) << 16) + acc_i * CV_BN;
                 if (!does_l) {
                     // R[h][x][d]: lanes are left pixels w = w0 + 32q + lane, columns right pixels x = x0c + n, d = w - x
-                    cv_store_quarter<+1>(R, t_s, rowbase, x0c - dbase, w0 + 32 * q - x0c, w0 + 32 * q + lane < W, W, D, Dp);
+                    cv_store_quarter<+1>(R, taddr, rowbase, x0c - dbase, w0 + 32 * q - x0c, w0 + 32 * q + lane < W, W, D, Dp);
                 } else {
-                    // L[h][w][d]: lanes are right pixels x = x0c + 32q + lane, columns left pixels w = w0 + n, d = w - x
-                    cv_store_quarter<-1>(L, t_t, rowbase, w0, w0 - x0c - 32 * q, true, W, D, Dp);
+#pragma unroll 1
+                    for (int j = 0; j < CV_BN / 32; j++) {
+                        const int base = w0 + 32 * q - (x0c + 32 * j);                 // d of (lane 0, column 0)
+                        if (base + 31 < 0 || base - 31 >= D) continue;                 // (warp uniform)
+                        unsigned v[32];
+                        tc_tmem_ld32(taddr + 32 * j, v);
+                        __syncwarp();                                                  // the previous flush has read the ring
+                        const int dl4 = (base + lane) << 2;
+#pragma unroll
+                        for (int i = 0; i < 32; i++) cv_sts(ring | ((dl4 - 4 * i) & (CV_RING * 4 - 4)), v[i]);
+                        __syncwarp();
+                        // the line [32 m, 32 m + 32) with m = floor(d of column 0 / 32) is complete for every pixel now:
+                        // 4 pixels per instruction (p = 4 k + sub), 8 float4 pieces per pixel
+                        const unsigned rq = tc_smem_u32(sm.l_ring[q]) + ((sub * CV_RING + 4 * l8) << 2);
+                        const int wq = w0 + 32 * q + sub;                               // left pixel of k = 0
+                        float *lrow = L + (rowbase + wq) * (size_t)Dp + 4 * l8;
+                        const int t0 = base + sub;
+                        float4 o[8];
+                        int off[8];
+#pragma unroll
+                        for (int k = 0; k < 8; k++) {
+                            const int dm = (t0 + 4 * k) & ~31;                          // 32 m (negative = band over)
+                            const bool on = dm >= 0 && dm + 4 * l8 < Dp && wq + 4 * k < W;
+                            off[k] = on ? 4 * k * Dp + dm : -1;
+                            if (on) o[k] = cv_lds128(rq + ((4 * k * CV_RING + (dm & 32)) << 2));
+                        }
+#pragma unroll
+                        for (int k = 0; k < 8; k++)
+                            if (off[k] >= 0) *reinterpret_cast<float4 *>(lrow + off[k]) = o[k];
+                    }
                 }
                 asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
-                tc_mbar_arrive(&sm.bar_empty[buf]);
+                tc_mbar_arrive(&sm.bar_empty[acc_i]);
             }
         }
     }
@@ -295,7 +349,7 @@ static int cost_volume_slab(const float *fl, const float *fr, float *L, float *R
     CvMaps maps;
     int rc = tc_encode_map_3d(maps.fl, fl, CV_C, W, H, 32, CV_BM, true, "cost_volume");
     if (rc) return rc;
-    rc = tc_encode_map_3d(maps.fr, fr, CV_C, W, H, 32, CV_BM, true, "cost_volume");
+    rc = tc_encode_map_3d(maps.fr, fr, CV_C, W, H, 32, CV_BN, true, "cost_volume");
     if (rc) return rc;
     // per device, asked on every call (no process-wide caches: one process may drive several GPUs)
     int dev = 0, num_sms = 0;
