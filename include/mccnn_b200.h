@@ -83,6 +83,9 @@ int mccnn_cost_volume(const float *fl, const float *fr, float *L, float *R,
  * arms [H][W][4] u8 = {up, down, left, right}; count [H][W] i32 = |U(h,w)|. */
 int mccnn_cross_arms(const float *img, uint8_t *arms, int32_t *count, int H, int W,
                      float intensity_threshold, int distance_threshold, void *stream);
+/* sum[0] (device, 8 bytes) = sum over the image of up + down: the host-side choice between the two bit-identical
+ * separable aggregation schedules reads this one number back (process_functional.cbca_auto_mode). */
+int mccnn_arms_vertical_sum(const uint8_t *arms, int H, int W, unsigned long long *sum, void *stream);
 /* The reference's explicit list: region [H][W][(2*dist)^2][2] i32 padded with -1 (pf:638-655). */
 int mccnn_cross_region_list(const uint8_t *arms, int32_t *region, int H, int W,
                             int distance_threshold, void *stream);

@@ -29,6 +29,7 @@ SIGNATURES = {
     "mccnn_cost_volume": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "mccnn_cross_arms": (_i, [_vp, _vp, _vp, _i, _i, _f, _i, _vp]),
     "mccnn_cross_region_list": (_i, [_vp, _vp, _i, _i, _i, _vp]),
+    "mccnn_arms_vertical_sum": (_i, [_vp, _i, _i, _vp, _vp]),
     "mccnn_cbca": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "mccnn_cbca_wta": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
     "mccnn_sgm_scratch_bytes": (_sz, [_i, _i, _i]),

@@ -48,6 +48,17 @@ __global__ void k_cross_count(const uchar4 *__restrict__ arms, int32_t *__restri
     count[(size_t)h * W + w] = n;
 }
 
+// sum over the image of up + down (what decides between the two bit-identical separable schedules, process_functional.py)
+__global__ void k_arms_vertical_sum(const uchar4 *__restrict__ arms, unsigned long long *__restrict__ sum, long long P) {
+    unsigned v = 0;
+    for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < P; p += (long long)gridDim.x * blockDim.x) {
+        const uchar4 a = arms[p];
+        v += (unsigned)a.x + (unsigned)a.y;
+    }
+    v = __reduce_add_sync(0xffffffffu, v);
+    if ((threadIdx.x & 31) == 0 && v) atomicAdd(sum, (unsigned long long)v);
+}
+
 // Compatibility view: the reference's explicit list, in its own order (pf:640-655).
 __global__ void k_cross_region_list(const uchar4 *__restrict__ arms, int32_t *__restrict__ region, int H, int W,
                                     int max_num) {
@@ -247,6 +258,16 @@ int mccnn_cross_arms(const float *img, uint8_t *arms, int32_t *count, int H, int
     MCCNN_LAUNCHED("cross_arms");
     k_cross_count<<<grid, block, 0, s>>>(reinterpret_cast<const uchar4 *>(arms), count, H, W);
     MCCNN_LAUNCHED("cross_count");
+    return MCCNN_OK;
+}
+
+int mccnn_arms_vertical_sum(const uint8_t *arms, int H, int W, unsigned long long *sum, void *stream) {
+    MCCNN_REQUIRE(arms && sum && H >= 1 && W >= 1, "arms_vertical_sum: bad arguments");
+    cudaStream_t s = (cudaStream_t)stream;
+    MCCNN_CUDA(cudaMemsetAsync(sum, 0, sizeof(unsigned long long), s));
+    const long long P = (long long)H * W;
+    k_arms_vertical_sum<<<(int)(P < 148 * 1024 ? (P + 255) / 256 : 592), 256, 0, s>>>(reinterpret_cast<const uchar4 *>(arms), sum, P);
+    MCCNN_LAUNCHED("arms_vertical_sum");
     return MCCNN_OK;
 }
 

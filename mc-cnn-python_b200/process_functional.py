@@ -49,7 +49,9 @@ def cbca_auto_mode(arms):
     """CBCA_SEPARABLE (chained rounds) for natural images, CBCA_SEPARABLE_TWO_PASS when the vertical arms are long.
     Reads one number back from the device (a host synchronisation of a few tens of microseconds per image)."""
     H, W = int(arms.shape[0]), int(arms.shape[1])
-    mean_vertical = float(arms[:, :, 0:2].sum(dtype=_torch().float64).item()) / float(H * W)
+    total = _torch().empty(1, dtype=_torch().int64, device=arms.device)
+    _ffi.call("mccnn_arms_vertical_sum", _ffi.ptr(arms), H, W, _ffi.ptr(total), _ffi.stream_ptr())
+    mean_vertical = float(total.item()) / float(H * W)
     return CBCA_SEPARABLE if mean_vertical < CBCA_AUTO_MEAN_VERTICAL_ARMS else CBCA_SEPARABLE_TWO_PASS
 
 

@@ -14,5 +14,5 @@ for k in k_cost_volume_tc; do
   timeout 600 ncu --set full --clock-control none --import-source on -k regex:$k -s 1 -c 1 -o gpurun_out/r2f_$k -f python scripts/profile_step.py 2 > gpurun_out/ncu_$k.log 2>&1
   tail -1 gpurun_out/ncu_$k.log
 done
-timeout 900 ncu --set full --clock-control none -k regex:'k_conv1|k_conv_prep|k_cost_fill|k_cross_arms|k_cross_count|k_sgm_flags|k_lr_labels|k_lr_fill|k_subpixel|k_median|k_bilateral' -c 24 -o gpurun_out/r2f_small_kernels -f python scripts/profile_step.py 1 > gpurun_out/ncu_small.log 2>&1
+timeout 900 ncu --set full --clock-control none -k regex:'k_conv1|k_conv_prep|k_cost_fill|k_cross_arms|k_cross_count|k_sgm_flags|k_wta_decode|k_lr_labels|k_lr_fill|k_subpixel|k_median|k_bilateral' -c 24 -o gpurun_out/r2f_small_kernels -f python scripts/profile_step.py 1 > gpurun_out/ncu_small.log 2>&1
 tail -1 gpurun_out/ncu_small.log
