@@ -7,6 +7,7 @@
 // HWD layout makes that walk cheap: the lanes of a warp are the disparities of one or two
 // pixels, so every lane follows the same arms (no divergence) and every load is a contiguous
 // 16 B granule of the neighbour pixel's disparity row (fully coalesced for any region shape).
+#include <stdlib.h>
 #include "common.cuh"
 #include "cbca_stream.cuh"
 #include "cbca_chain.cuh"
@@ -178,7 +179,7 @@ typedef CgShape<22, 192, 4, 3> CgG3;         // 55 KB, 4 CTAs of 6 warps per SM
 
 template <class C>
 static int launch_colrow_g(const float *hs_in, float *hs_out, const uint8_t *arms, const int32_t *count, int G, int H, int W,
-                           cudaStream_t s) {
+                           int settled, cudaStream_t s) {
     CUtensorMap map, map_row;
     int rc = tc_encode_map_3d(map, hs_in, (unsigned long long)G * 4, W, H, CS_GC * 4 * C::GPT, C::NP, false, "cbca", 3);
     if (rc) return rc;
@@ -189,7 +190,7 @@ static int launch_colrow_g(const float *hs_in, float *hs_out, const uint8_t *arm
     MCCNN_CUDA(cudaFuncSetAttribute(k_cbca_colrow_g<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
     dim3 grid(cdiv(G, CS_GC * C::GPT), cdiv(W, C::S), H);
     k_cbca_colrow_g<C><<<grid, C::NT, C::SMEM, s>>>(map, map_row, reinterpret_cast<const float4 *>(hs_in), reinterpret_cast<float4 *>(hs_out),
-                                                    reinterpret_cast<const uchar4 *>(arms), count, G, H, W, ahead);
+                                                    reinterpret_cast<const uchar4 *>(arms), count, G, H, W, ahead, settled);
     MCCNN_LAUNCHED("cbca_colrow");
     return MCCNN_OK;
 }
@@ -209,10 +210,10 @@ static int colrow_gpt(int G, int hm) {
 }
 
 static int launch_colrow(int gpt, const float *hs_in, float *hs_out, const uint8_t *arms, const int32_t *count, int G, int H, int W,
-                         cudaStream_t s) {
-    if (gpt == 3) return launch_colrow_g<CgG3>(hs_in, hs_out, arms, count, G, H, W, s);
-    if (gpt == 2) return launch_colrow_g<CgG2>(hs_in, hs_out, arms, count, G, H, W, s);
-    return launch_colrow_g<CgG1>(hs_in, hs_out, arms, count, G, H, W, s);
+                         int settled, cudaStream_t s) {
+    if (gpt == 3) return launch_colrow_g<CgG3>(hs_in, hs_out, arms, count, G, H, W, settled, s);
+    if (gpt == 2) return launch_colrow_g<CgG2>(hs_in, hs_out, arms, count, G, H, W, settled, s);
+    return launch_colrow_g<CgG1>(hs_in, hs_out, arms, count, G, H, W, settled, s);
 }
 
 // n >= 2 rounds, chained: rows | (n-1) x colrow | cols.  The row sums ping-pong between `out` and `scratch` so that
@@ -227,7 +228,9 @@ static int chained_rounds(const float *in, float *out, float *scratch, const CsS
                                                                 reinterpret_cast<const uchar4 *>(arms), count, G, H, W);
     MCCNN_LAUNCHED("cbca_rows");
     for (int k = 1; k < iters; k++) {
-        int rc = launch_colrow(gpt, hs[(k - 1) & 1], hs[k & 1], arms, count, G, H, W, s);
+        // hs[k & 1] was last written two passes ago (k = 2: by the row pass): from k = 2 on, pixels without arms are settled
+        static const bool no_skip = getenv("MCCNN_CBCA_NO_SETTLED") != nullptr;
+        int rc = launch_colrow(gpt, hs[(k - 1) & 1], hs[k & 1], arms, count, G, H, W, k >= 2 && !no_skip, s);
         if (rc) return rc;
     }
     return closing_cols(scratch, out, sc, wt, arms, count, G, H, W, s);
