@@ -7,7 +7,6 @@
 // HWD layout makes that walk cheap: the lanes of a warp are the disparities of one or two
 // pixels, so every lane follows the same arms (no divergence) and every load is a contiguous
 // 16 B granule of the neighbour pixel's disparity row (fully coalesced for any region shape).
-#include <stdlib.h>
 #include "common.cuh"
 #include "cbca_stream.cuh"
 #include "cbca_chain.cuh"
@@ -167,6 +166,7 @@ static int two_pass_rounds(const float *in, float *out, float *scratch, const Cs
 
 // The chained round's shapes (cbca_chain.cuh): pixels per segment, threads, resident CTAs asked for, granules per thread.
 // Measured at 1024 x 1024, natural image, ms per round of a 16-round call (B200):
+// (all before pixels without arms were dropped from the passes that find them settled: G3 is 0.269 on those, 0.333 on the first)
 //   ndisp 192 (48 granules): G1 0.362, G3 0.333 (other GPT = 3 shapes: 14 px x 128 thr 0.334, 30 x 256 0.338, 22 x 128 0.356,
 //                            30 x 128 0.383; without the L2 look-ahead G3 is 0.364); round 2's first cp.async kernel 0.438,
 //                            two streaming passes 0.580
@@ -229,8 +229,7 @@ static int chained_rounds(const float *in, float *out, float *scratch, const CsS
     MCCNN_LAUNCHED("cbca_rows");
     for (int k = 1; k < iters; k++) {
         // hs[k & 1] was last written two passes ago (k = 2: by the row pass): from k = 2 on, pixels without arms are settled
-        static const bool no_skip = getenv("MCCNN_CBCA_NO_SETTLED") != nullptr;
-        int rc = launch_colrow(gpt, hs[(k - 1) & 1], hs[k & 1], arms, count, G, H, W, k >= 2 && !no_skip, s);
+        int rc = launch_colrow(gpt, hs[(k - 1) & 1], hs[k & 1], arms, count, G, H, W, k >= 2, s);
         if (rc) return rc;
     }
     return closing_cols(scratch, out, sc, wt, arms, count, G, H, W, s);

@@ -70,15 +70,15 @@ struct CgShape {
 template <class C>
 __device__ __forceinline__ bool cc_pixel_info(const uchar4 *__restrict__ arms, const int32_t *__restrict__ count, const size_t rowp,
                                               const int w0, const int tid, const int p_lo, const int np, const int sv,
-                                              const unsigned sP, int &lneed, int &rneed) {
+                                              const unsigned sP, int &lneed, int &rneed, unsigned &packed) {
     constexpr int HL = C::HL;
-    lneed = 0; rneed = 0;
+    lneed = 0; rneed = 0; packed = 0;
     if (tid >= p_lo && tid < np) {
         const size_t q = rowp + w0 - HL + tid;
         const uchar4 a = arms[q];
         const float n = (float)count[q];
-        cc_sts128u(sP + tid * 16, make_uint4((unsigned)a.x | (unsigned)a.y << 8 | (unsigned)a.z << 16 | (unsigned)a.w << 24,
-                                             __float_as_uint(n), __float_as_uint(1.0f / n), 0u));
+        packed = (unsigned)a.x | (unsigned)a.y << 8 | (unsigned)a.z << 16 | (unsigned)a.w << 24;
+        cc_sts128u(sP + tid * 16, make_uint4(packed, __float_as_uint(n), __float_as_uint(1.0f / n), 0u));
         const int px = tid - HL;
         if (px >= 0 && px < sv) { lneed = (int)a.z - px; rneed = (int)a.w - (sv - 1 - px); }
     }
@@ -122,9 +122,11 @@ __global__ void __launch_bounds__(C::NT, C::MINB) k_cbca_colrow_g(const __grid_c
                                                                   const int32_t *__restrict__ count, int G, int H, int W, int ahead,
                                                                   int settled) {
     constexpr int S = C::S, NP = C::NP, HL = C::HL, GPT = C::GPT, PB = C::PB, SLOTS = C::SLOTS;
-    static_assert(NP <= 32 && NP % SLOTS == 0 && C::NT >= 64, "one warp makes the per-pixel information; whole sweeps of the pixel slots");
+    static_assert(NP <= 32 && C::NT >= 64, "one warp makes the per-pixel information; whole sweeps of the pixel slots");
     extern __shared__ __align__(128) unsigned char cc_raw[];
     __shared__ int reach[2];
+    __shared__ int nlive;
+    __shared__ unsigned char live[32];                                // staged pixels that have work this round, compacted
     __shared__ __align__(8) unsigned long long bar;
     const unsigned sU = (unsigned)__cvta_generic_to_shared(cc_raw);   // [NP][PB]  Hs_k(h-1)
     const unsigned sT = sU + NP * PB;                                 // [NP][PB]  Hs_k(h), then out_k
@@ -158,21 +160,30 @@ __global__ void __launch_bounds__(C::NT, C::MINB) k_cbca_colrow_g(const __grid_c
     const unsigned my = gi * 16;
     int lneed, rneed;
     // (the last warp, so that its loads are not queued behind thread 0's TMA set-up)
-    const bool far = cc_pixel_info<C>(arms, count, rowp, w0, tid - (C::NT - 32), p_lo, np, sv, sP, lneed, rneed);
+    unsigned packed;
+    const int ti = tid - (C::NT - 32);
+    const bool far = cc_pixel_info<C>(arms, count, rowp, w0, ti, p_lo, np, sv, sP, lneed, rneed, packed);
+    if (ti >= 0) {
+        // A pixel whose four arms are all zero is its own region: out_k = Hs_k = out_{k-1}, bit for bit, in every round.
+        // From the third pass over the volume on (settled) both ping-pong buffers hold that value: T already is out_k and
+        // there is nothing to store -- on a natural image that is every second pixel.  The pixels that do have work are
+        // compacted into a list, so the two phases sweep over half as many.
+        const bool on = ti >= p_lo && ti < np && !(settled && packed == 0);
+        const unsigned m = __ballot_sync(0xffffffffu, on);
+        if (on) live[__popc(m & ((1u << ti) - 1u))] = (unsigned char)ti;
+        if (ti == 0) nlive = __popc(m);
+    }
     const int any_far = __syncthreads_or(far);                        // publishes the per-pixel information and the mbarrier
     tc_mbar_wait(&bar, 0);
 
     // ---- column phase: out_k of the staged pixels into T
+    const int nl_ = nlive;
     if (jm) {
-        unsigned t = sT + slot * PB + my, pa = sP + slot * 16;
 #pragma unroll 1
-        for (int p = slot; p < np; p += SLOTS, t += SLOTS * PB, pa += SLOTS * 16) {
-            if (p < p_lo) continue;
-            const uint4 pi = cc_lds128u(pa);
-            // A pixel whose four arms are all zero is its own region: out_k = Hs_k = out_{k-1}, bit for bit, in every round.
-            // From the third pass over the volume on (settled) both ping-pong buffers hold that value: T already is out_k
-            // here and the row phase below has nothing to store -- on a natural image that is every second pixel.
-            if (settled && pi.x == 0) continue;
+        for (int i = slot; i < nl_; i += SLOTS) {
+            const int p = live[i];
+            const unsigned t = sT + p * PB + my;
+            const uint4 pi = cc_lds128u(sP + p * 16);
             const int up = pi.x & 0xff, down = (pi.x >> 8) & 0xff;
             float4 acc[GPT];
 #pragma unroll
@@ -221,14 +232,15 @@ __global__ void __launch_bounds__(C::NT, C::MINB) k_cbca_colrow_g(const __grid_c
 
     // ---- row phase: Hs_{k+1} of the segment from shared memory
     if (jm) {
-        char *out = reinterpret_cast<char *>(dst + (rowp + w0 + slot) * G + g);
-        const ptrdiff_t stepB = (ptrdiff_t)SLOTS * G * 16;
-        unsigned t0 = sT + (slot + HL) * PB + my, pa = sP + (slot + HL) * 16;
+        float4 *out0 = dst + (rowp + w0) * G + g;
 #pragma unroll 1
-        for (int px = slot; px < sv; px += SLOTS, t0 += SLOTS * PB, pa += SLOTS * 16, out += stepB) {
+        for (int i = slot; i < nl_; i += SLOTS) {
+            const int p = live[i], px = p - HL;
+            if (px < 0 || px >= sv) continue;                             // (a halo pixel)
+            const unsigned t0 = sT + p * PB + my;
+            float4 *out = out0 + (ptrdiff_t)px * G;
             unsigned a;
-            asm volatile("ld.shared.u32 %0, [%1];\n" : "=r"(a) : "r"(pa));
-            if (settled && a == 0) continue;
+            asm volatile("ld.shared.u32 %0, [%1];\n" : "=r"(a) : "r"(sP + p * 16));
             float4 acc[GPT];
 #pragma unroll
             for (int j = 0; j < GPT; j++) { acc[j] = make_float4(0.f, 0.f, 0.f, 0.f); cs_add(acc[j], cc_lds128(t0 + j * 256)); }
@@ -247,7 +259,7 @@ __global__ void __launch_bounds__(C::NT, C::MINB) k_cbca_colrow_g(const __grid_c
             }
 #pragma unroll
             for (int j = 0; j < GPT; j++)
-                if ((jm >> j) & 1) reinterpret_cast<float4 *>(out)[CS_GC * j] = acc[j];
+                if ((jm >> j) & 1) out[CS_GC * j] = acc[j];
         }
     }
 }
