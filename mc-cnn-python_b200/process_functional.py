@@ -38,10 +38,10 @@ CBCA_SEPARABLE, CBCA_EXACT, CBCA_SEPARABLE_TWO_PASS = 0, 1, 2
 # Host-side default: pick 0 or 2 per image from the arms (the two are bit-identical, only their speed differs).  The
 # chained kernel gathers the rows beyond +-1 of a vertical arm from global memory behind a CTA barrier and recomputes
 # the horizontal halo of its segments, both of which grow with the arms: measured at 1024x1024x192, ms per round,
-# natural image (mean up + down = 0.96) 0.44 chained / 0.58 two passes, piece-wise constant image (22.1) 2.65 / 1.85;
-# linear in the mean, the two meet at 3.5.
+# natural image (mean up + down = 0.96) 0.29 chained / 0.58 two passes, piece-wise constant image (22.1) 2.20 / 1.85;
+# linear in the mean, the two meet at 10.
 CBCA_AUTO = -1
-CBCA_AUTO_MEAN_VERTICAL_ARMS = 3.5
+CBCA_AUTO_MEAN_VERTICAL_ARMS = 10.0
 CBCA_MODE = CBCA_AUTO
 
 

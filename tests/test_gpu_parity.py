@@ -306,6 +306,28 @@ def test_cbca_chained_rounds_match_two_pass(pf, monkeypatch):
         assert eq(Ls, Lt) and eq(Rs, Rt), (H, W, D, levels, iters, dist)
 
 
+def test_cbca_settled_pixels_keep_the_bits_of_the_two_pass_form(pf, monkeypatch):
+    """From the third pass of a chained call on, pixels without arms are skipped (both ping-pong buffers hold their value).
+    Signed zeros, infinities and NaNs in such pixels, many rounds, every granules-per-thread shape: same bits as two
+    passes per round, which never skip anything."""
+    for (H, W, D, levels, iters) in [(40, 90, 192, 40, 9), (33, 70, 256, 25, 7), (24, 64, 20, 60, 16), (16, 50, 400, 30, 5)]:
+        li, ri = synth_images(7 * H + D, H, W, levels, 2)
+        rng = np.random.default_rng(H)
+        Lv = (rng.integers(-3, 4, (D, H, W)) * 0.5).astype(np.float32)          # exact zeros among the values
+        Lv[rng.random(Lv.shape) < 0.05] *= -0.0                                # ... of both signs
+        Lv[:, 3, 5] = np.inf
+        Lv[:, 7, 11] = np.nan
+        Rv = -Lv
+        arms, _ = pf.cross_arms(li, 0.02, 14)
+        assert float((arms.reshape(-1, 4).sum(1) == 0).float().mean()) > 0.1, "the case needs pixels without arms"
+        monkeypatch.setattr(pf, "CBCA_MODE", pf.CBCA_SEPARABLE_TWO_PASS)
+        Ls, Rs = pf.cost_volume_aggregation(li, ri, Lv, Rv, 0.02, 14, iters)
+        monkeypatch.setattr(pf, "CBCA_MODE", pf.CBCA_SEPARABLE)
+        Lt, Rt = pf.cost_volume_aggregation(li, ri, Lv, Rv, 0.02, 14, iters)
+        bits = lambda a: np.ascontiguousarray(a).view(np.uint32)
+        assert eq(bits(Ls), bits(Lt)) and eq(bits(Rs), bits(Rt)), (H, W, D, iters)
+
+
 def test_cbca_auto_mode_follows_the_vertical_arms(pf, pkg):
     """The host-side default picks the chained rounds for natural images and two passes per round when the vertical arms
     are long (piece-wise constant images); either way the bits are the same."""
