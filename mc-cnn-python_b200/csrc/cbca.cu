@@ -209,6 +209,34 @@ static int colrow_gpt(int G, int hm) {
     return best;
 }
 
+template <class C>
+static int launch_close_g(const float *hs_in, float *out, const CsWta *wt, const uint8_t *arms, const int32_t *count, int G, int H,
+                          int W, cudaStream_t s) {
+    CUtensorMap map, map_row;
+    int rc = tc_encode_map_3d(map, hs_in, (unsigned long long)G * 4, W, H, CS_GC * 4 * C::GPT, C::NP, false, "cbca", 3);
+    if (rc) return rc;
+    rc = tc_encode_map_3d(map_row, hs_in, (unsigned long long)G * 4, W, H, CS_GC * 4 * C::GPT, C::NP, false, "cbca", 1);
+    if (rc) return rc;
+    MCCNN_CUDA(cudaFuncSetAttribute(k_cbca_close_g<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
+    CsWta w = CsWta();
+    if (wt) {
+        w = *wt;
+        MCCNN_CUDA(cudaMemsetAsync(w.keys, 0xff, (size_t)H * W * sizeof(unsigned long long), s));
+    }
+    dim3 grid(cdiv(G, CS_GC * C::GPT), cdiv(W, C::S), H);
+    k_cbca_close_g<C><<<grid, C::NT, C::SMEM, s>>>(map, map_row, reinterpret_cast<const float4 *>(hs_in), reinterpret_cast<float4 *>(out),
+                                                   reinterpret_cast<const uchar4 *>(arms), count, G, H, W, 8, 1, wt ? wt->store : 1, w);
+    MCCNN_LAUNCHED("cbca_close");
+    return MCCNN_OK;
+}
+
+static int launch_close(int gpt, const float *hs_in, float *out, const CsWta *wt, const uint8_t *arms, const int32_t *count, int G, int H,
+                        int W, cudaStream_t s) {
+    if (gpt == 3) return launch_close_g<CgG3>(hs_in, out, wt, arms, count, G, H, W, s);
+    if (gpt == 2) return launch_close_g<CgG2>(hs_in, out, wt, arms, count, G, H, W, s);
+    return launch_close_g<CgG1>(hs_in, out, wt, arms, count, G, H, W, s);
+}
+
 static int launch_colrow(int gpt, const float *hs_in, float *hs_out, const uint8_t *arms, const int32_t *count, int G, int H, int W,
                          int settled, cudaStream_t s) {
     if (gpt == 3) return launch_colrow_g<CgG3>(hs_in, hs_out, arms, count, G, H, W, settled, s);
@@ -232,7 +260,9 @@ static int chained_rounds(const float *in, float *out, float *scratch, const CsS
         int rc = launch_colrow(gpt, hs[(k - 1) & 1], hs[k & 1], arms, count, G, H, W, k >= 2, s);
         if (rc) return rc;
     }
-    return closing_cols(scratch, out, sc, wt, arms, count, G, H, W, s);
+    if (sc) return closing_cols(scratch, out, sc, wt, arms, count, G, H, W, s);
+    // `out` was last written two passes ago (iters = 2: by the row pass): it already holds the pixels without arms
+    return launch_close(gpt, scratch, out, wt, arms, count, G, H, W, s);
 }
 
 // the default: chained rounds wherever they apply (two rounds or more; the shared-memory tile grows with the arm limit)

@@ -264,4 +264,114 @@ __global__ void __launch_bounds__(C::NT, C::MINB) k_cbca_colrow_g(const __grid_c
     }
 }
 
+// The closing pass of a chained call in the same style: out_n = colsum(Hs_n) / |U| for a segment, straight to the volume,
+// with the winner-take-all of pf:239-272 folded in (wt.keys != NULL).  A thread holds 4 * GPT disparities of a pixel, so
+// the first-minimum search costs a third of what it does with one granule per thread (k_cbca_pass<cols, WT>), and at
+// ndisp <= 64 * GPT one CTA sees the whole disparity row.  The smallest cost of the pixel over the CTA's disparities, then
+// the first disparity that has it (cells d >= D do not exist; NaN and +inf never win, -0 = +0: k_wta's rules), merged into
+// the per-pixel 64-bit key with one atomicMin.  Pixels without arms (armless != 0: the call had >= 2 rounds, so `dst`
+// already holds their value, see k_cbca_colrow_g) are read for the minimum but neither recomputed nor stored.
+template <class C>
+__global__ void __launch_bounds__(C::NT, C::MINB) k_cbca_close_g(const __grid_constant__ CUtensorMap map,
+                                                                 const __grid_constant__ CUtensorMap map_row,
+                                                                 const float4 *__restrict__ src, float4 *__restrict__ dst,
+                                                                 const uchar4 *__restrict__ arms, const int32_t *__restrict__ count,
+                                                                 int G, int H, int W, int ahead, int armless, int store, const CsWta wt) {
+    constexpr int S = C::S, NP = C::NP, HL = C::HL, GPT = C::GPT, PB = C::PB, SLOTS = C::SLOTS;
+    extern __shared__ __align__(128) unsigned char cc_raw[];
+    __shared__ __align__(8) unsigned long long bar;
+    const unsigned sU = (unsigned)__cvta_generic_to_shared(cc_raw);
+    const unsigned sT = sU + NP * PB, sP = sU + 3 * NP * PB;
+    const int tid = threadIdx.x, gi = tid & 15, slot = tid >> 4;
+    const int g = blockIdx.x * (CS_GC * GPT) + gi, w0 = blockIdx.y * S, h = blockIdx.z;
+    if (tid == 0) {
+        tc_mbar_init(&bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+        tc_mbar_expect_tx(&bar, 3 * NP * PB);
+        tc_tma_load_3d(cc_raw, &map, blockIdx.x * (CS_GC * GPT * 4), w0 - HL, h - 1, &bar);
+        if (ahead > 0 && h + 1 + ahead < H)
+            asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];\n" ::"l"(
+                             reinterpret_cast<unsigned long long>(&map_row)),
+                         "r"((int)(blockIdx.x * (CS_GC * GPT * 4))), "r"(w0 - HL), "r"(h + 1 + ahead)
+                         : "memory");
+    }
+    unsigned jm = 0;
+#pragma unroll
+    for (int j = 0; j < GPT; j++) jm |= (g + CS_GC * j < G ? 1u : 0u) << j;
+    const int sv = min(S, W - w0);
+    const int np = min(NP, W - w0 + HL);
+    const int p_lo = w0 > 0 ? 0 : HL;
+    const ptrdiff_t stride = (ptrdiff_t)W * G;
+    const size_t rowp = (size_t)h * W;
+    const float4 *cbase = src + (rowp + w0 - HL) * G + g;
+    const unsigned my = gi * 16;
+    int lneed, rneed;
+    unsigned packed;
+    cc_pixel_info<C>(arms, count, rowp, w0, tid - (C::NT - 32), p_lo, np, sv, sP, lneed, rneed, packed);
+    __syncthreads();                                                  // publishes the per-pixel information and the mbarrier
+    tc_mbar_wait(&bar, 0);
+
+    float4 *out0 = dst + (rowp + w0) * G + g;
+    unsigned long long *keys = wt.keys ? wt.keys + rowp + w0 : nullptr;
+    // (every lane makes every sweep: the shuffles below need the whole warp)
+#pragma unroll 1
+    for (int px0 = 0; px0 < sv; px0 += SLOTS) {
+        const int px = px0 + slot, p = px + HL;
+        const bool valid = px < sv;
+        float4 acc[GPT];
+        bool keep = false;                                            // armless and settled: nothing to compute or store
+        if (valid) {
+            const unsigned t = sT + p * PB + my;
+            const uint4 pi = cc_lds128u(sP + p * 16);
+            keep = armless && pi.x == 0;
+            const int up = pi.x & 0xff, down = (pi.x >> 8) & 0xff;
+#pragma unroll
+            for (int j = 0; j < GPT; j++) { acc[j] = make_float4(0.f, 0.f, 0.f, 0.f); cs_add(acc[j], cc_lds128(t + j * 256)); }
+            if (!keep && jm) {
+                if (up >= 1) {
+#pragma unroll
+                    for (int j = 0; j < GPT; j++) cs_add(acc[j], cc_lds128(t - NP * PB + j * 256));
+                    if (up >= 2) cg_walk<GPT>(acc, cbase + (ptrdiff_t)p * G, -stride, 2, up, jm);
+                }
+                if (down >= 1) {
+#pragma unroll
+                    for (int j = 0; j < GPT; j++) cs_add(acc[j], cc_lds128(t + NP * PB + j * 256));
+                    if (down >= 2) cg_walk<GPT>(acc, cbase + (ptrdiff_t)p * G, stride, 2, down, jm);
+                }
+                cg_divide<GPT>(acc, __uint_as_float(pi.y), __uint_as_float(pi.z));
+#pragma unroll
+                for (int j = 0; j < GPT; j++)
+                    if (store && ((jm >> j) & 1)) out0[(ptrdiff_t)px * G + CS_GC * j] = acc[j];
+            }
+        }
+        if (keys) {
+            float m = CUDART_INF_F;
+#pragma unroll
+            for (int j = 0; j < GPT; j++) {
+                const int d0 = (g + CS_GC * j) << 2;
+                const bool on = valid && ((jm >> j) & 1);
+                if (!on) acc[j] = make_float4(CUDART_INF_F, CUDART_INF_F, CUDART_INF_F, CUDART_INF_F);
+                if (d0 + 1 >= wt.D) acc[j].y = CUDART_INF_F;
+                if (d0 + 2 >= wt.D) acc[j].z = CUDART_INF_F;
+                if (d0 + 3 >= wt.D) acc[j].w = CUDART_INF_F;
+                m = fminf(m, fminf(fminf(acc[j].x, acc[j].y), fminf(acc[j].z, acc[j].w)));
+            }
+#pragma unroll
+            for (int off = 8; off >= 1; off >>= 1) m = fminf(m, __shfl_xor_sync(0xffffffffu, m, off));
+            unsigned bd = 0xffffffffu;
+#pragma unroll
+            for (int j = GPT - 1; j >= 0; j--) {
+                const unsigned d0 = (unsigned)(g + CS_GC * j) << 2;
+                bd = acc[j].w == m ? d0 + 3 : bd;
+                bd = acc[j].z == m ? d0 + 2 : bd;
+                bd = acc[j].y == m ? d0 + 1 : bd;
+                bd = acc[j].x == m ? d0 : bd;
+            }
+#pragma unroll
+            for (int off = 8; off >= 1; off >>= 1) bd = min(bd, __shfl_xor_sync(0xffffffffu, bd, off));
+            if (gi == 0 && valid && m < CUDART_INF_F) atomicMin(keys + px, (unsigned long long)cs_fkey(m + 0.0f) << 32 | bd);
+        }
+    }
+}
+
 }  // namespace mccnn

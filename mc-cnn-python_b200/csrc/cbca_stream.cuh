@@ -72,7 +72,7 @@ __device__ __forceinline__ unsigned cs_fkey(float f) {             // order-pres
 }
 
 template <bool COLS, int ITEMS, int NB, bool SC = false, bool WT = false>
-__global__ void __launch_bounds__(CS_THREADS, CS_MIN_BLOCKS) k_cbca_pass(const float4 *__restrict__ src, float4 *__restrict__ dst,
+__global__ void __launch_bounds__(CS_THREADS, WT ? CS_MIN_BLOCKS - 2 : CS_MIN_BLOCKS) k_cbca_pass(const float4 *__restrict__ src, float4 *__restrict__ dst,
                                                           const uchar4 *__restrict__ arms, const int32_t *__restrict__ count,
                                                           int G, int H, int W, const CsScatter sc = CsScatter(),
                                                           const CsWta wt = CsWta()) {
@@ -82,7 +82,8 @@ __global__ void __launch_bounds__(CS_THREADS, CS_MIN_BLOCKS) k_cbca_pass(const f
     // pixel's 4*Dp bytes are fetched together (DRAM pages)
     const int bx = blockIdx.y, by = blockIdx.z;
     const int gi = threadIdx.x % CS_GC, g = blockIdx.x * CS_GC + gi;
-    if (g >= G) return;
+    if (!WT && g >= G) return;                                   // (with the winner-take-all every lane stays for the shuffles)
+    const bool gok = g < G;
     const ptrdiff_t stride = COLS ? (ptrdiff_t)W * G : (ptrdiff_t)G;
     size_t p[ITEMS];
     bool ok[ITEMS];
@@ -92,7 +93,7 @@ __global__ void __launch_bounds__(CS_THREADS, CS_MIN_BLOCKS) k_cbca_pass(const f
     for (int s = 0; s < ITEMS; s++) {
         const int pi = s * (CS_THREADS / CS_GC) + threadIdx.x / CS_GC;
         const int h = by * PH + pi / CS_PW, w = bx * CS_PW + pi % CS_PW;
-        ok[s] = h < H && w < W;
+        ok[s] = h < H && w < W && gok;
         p[s] = ok[s] ? (size_t)h * W + w : 0;
         if (ok[s]) {
             const float4 *c = src + p[s] * G + g;
@@ -110,44 +111,47 @@ __global__ void __launch_bounds__(CS_THREADS, CS_MIN_BLOCKS) k_cbca_pass(const f
     asm volatile("cp.async.wait_all;\n" ::: "memory");
 #pragma unroll
     for (int s = 0; s < ITEMS; s++) {
-        if (!ok[s]) continue;
-        const float4 *c = src + p[s] * G + g;
-        const int lo = COLS ? a[s].x : a[s].z, hi = COLS ? a[s].y : a[s].w;     // (up, down) | (left, right)
+        if (!WT && !ok[s]) continue;
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-        cs_add(acc, stage[0][s][threadIdx.x]);                   // x, x-1, .., x-lo, then x+1, .., x+hi (pf:640-650)
+        if (ok[s]) {
+            const float4 *c = src + p[s] * G + g;
+            const int lo = COLS ? a[s].x : a[s].z, hi = COLS ? a[s].y : a[s].w;     // (up, down) | (left, right)
+            cs_add(acc, stage[0][s][threadIdx.x]);                   // x, x-1, .., x-lo, then x+1, .., x+hi (pf:640-650)
 #pragma unroll
-        for (int k = 1; k <= NB; k++)
-            if (lo >= k) cs_add(acc, stage[2 * k - 1][s][threadIdx.x]);
-        for (int k = NB + 1; k <= lo; k++) cs_add(acc, c[-k * stride]);
+            for (int k = 1; k <= NB; k++)
+                if (lo >= k) cs_add(acc, stage[2 * k - 1][s][threadIdx.x]);
+            for (int k = NB + 1; k <= lo; k++) cs_add(acc, c[-k * stride]);
 #pragma unroll
-        for (int k = 1; k <= NB; k++)
-            if (hi >= k) cs_add(acc, stage[2 * k][s][threadIdx.x]);
-        for (int k = NB + 1; k <= hi; k++) cs_add(acc, c[k * stride]);
-        if (COLS) {
-            const float vmax = fmaxf(fmaxf(fabsf(acc.x), fabsf(acc.y)), fmaxf(fabsf(acc.z), fabsf(acc.w)));
-            const float vmin = fminf(fminf(fabsf(acc.x), fabsf(acc.y)), fminf(fabsf(acc.z), fabsf(acc.w)));
-            if (vmax < 1e30f && vmin > 1e-30f) {
-                const float y = 1.0f / n[s];
-                acc = make_float4(cs_div1(acc.x, n[s], y), cs_div1(acc.y, n[s], y), cs_div1(acc.z, n[s], y), cs_div1(acc.w, n[s], y));
-            } else {
-                acc = make_float4(acc.x / n[s], acc.y / n[s], acc.z / n[s], acc.w / n[s]);   // pf:161
+            for (int k = 1; k <= NB; k++)
+                if (hi >= k) cs_add(acc, stage[2 * k][s][threadIdx.x]);
+            for (int k = NB + 1; k <= hi; k++) cs_add(acc, c[k * stride]);
+            if (COLS) {
+                const float vmax = fmaxf(fmaxf(fabsf(acc.x), fabsf(acc.y)), fmaxf(fabsf(acc.z), fabsf(acc.w)));
+                const float vmin = fminf(fminf(fabsf(acc.x), fabsf(acc.y)), fminf(fabsf(acc.z), fabsf(acc.w)));
+                if (vmax < 1e30f && vmin > 1e-30f) {
+                    const float y = 1.0f / n[s];
+                    acc = make_float4(cs_div1(acc.x, n[s], y), cs_div1(acc.y, n[s], y), cs_div1(acc.z, n[s], y), cs_div1(acc.w, n[s], y));
+                } else {
+                    acc = make_float4(acc.x / n[s], acc.y / n[s], acc.z / n[s], acc.w / n[s]);   // pf:161
+                }
             }
         }
         if (WT) {
-            // this lane's first minimum (strict <, cells d >= D do not exist; NaN and +inf never win, as in k_wta)
+            // The pixel's smallest cost over the CTA's 64 disparities, then the first disparity that has it (cells d >= D do
+            // not exist; NaN and +inf never win, -0 = +0: k_wta's rules).  Xor shuffles stay inside the 16 lanes of a pixel and
+            // all 32 lanes take part (a reduction under a half-warp mask runs the two halves of the warp one after the other).
             const int d0 = g << 2;
-            float best = CUDART_INF_F;
-            int bd = 0;
-            if (acc.x < best) { best = acc.x; bd = d0; }
-            if (d0 + 1 < wt.D && acc.y < best) { best = acc.y; bd = d0 + 1; }
-            if (d0 + 2 < wt.D && acc.z < best) { best = acc.z; bd = d0 + 2; }
-            if (d0 + 3 < wt.D && acc.w < best) { best = acc.w; bd = d0 + 3; }
-            const unsigned half = 0xffffu << (threadIdx.x & 16);                   // the 16 lanes of this pixel
-            const unsigned k = best < CUDART_INF_F ? cs_fkey(best + 0.0f) : 0xffffffffu;   // (-0 counts as +0, like <)
-            const unsigned kmin = __reduce_min_sync(half, k);
-            const unsigned dmin = __reduce_min_sync(half, k == kmin ? (unsigned)bd : 0xffffffffu);
-            if (gi == 0 && kmin != 0xffffffffu) atomicMin(wt.keys + p[s], (unsigned long long)kmin << 32 | dmin);
+            const float vx = ok[s] ? acc.x : CUDART_INF_F, vy = ok[s] && d0 + 1 < wt.D ? acc.y : CUDART_INF_F;
+            const float vz = ok[s] && d0 + 2 < wt.D ? acc.z : CUDART_INF_F, vw = ok[s] && d0 + 3 < wt.D ? acc.w : CUDART_INF_F;
+            float m = fminf(fminf(vx, vy), fminf(vz, vw));
+#pragma unroll
+            for (int off = 8; off >= 1; off >>= 1) m = fminf(m, __shfl_xor_sync(0xffffffffu, m, off));
+            unsigned bd = vx == m ? d0 : vy == m ? d0 + 1 : vz == m ? d0 + 2 : vw == m ? d0 + 3 : 0xffffffffu;
+#pragma unroll
+            for (int off = 8; off >= 1; off >>= 1) bd = min(bd, __shfl_xor_sync(0xffffffffu, bd, off));
+            if (gi == 0 && ok[s] && m < CUDART_INF_F) atomicMin(wt.keys + p[s], (unsigned long long)cs_fkey(m + 0.0f) << 32 | bd);
         }
+        if (!ok[s]) continue;
         if (WT && !wt.store) continue;
         if (!SC) {
             dst[p[s] * G + g] = acc;

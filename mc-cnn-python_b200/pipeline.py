@@ -113,14 +113,21 @@ class StereoMatcher(object):
                 call("mccnn_cost_volume", p(feat[0]), p(feat[1]), p(vol[0]), p(vol[1]), H, W, 64, D, sp())
             return cost_volume
 
+        def make_arms_of(i):
+            def arms_of():
+                call("mccnn_cross_arms", p(img[i]), p(self.arms[i]), p(self.count[i]), H, W,
+                     f(np.float32(hp["cbca_intensity"])), int(hp["cbca_distance"]), sp())
+                # chained rounds or two passes per round: bit-identical, chosen per image from its arms (one number
+                # read back from the device: the only host synchronisation of the step)
+                self.cbca_modes[i] = _pf.cbca_auto_mode(self.arms[i]) if self.cbca_mode == _pf.CBCA_AUTO else self.cbca_mode
+            return arms_of
+
+        self._arms_fns = [make_arms_of(0), make_arms_of(1)]
+
         def make_arms():
             def arms():
-                for i in range(2):
-                    call("mccnn_cross_arms", p(img[i]), p(self.arms[i]), p(self.count[i]), H, W,
-                         f(np.float32(hp["cbca_intensity"])), int(hp["cbca_distance"]), sp())
-                    # chained rounds or two passes per round: bit-identical, chosen per image from its arms (one number
-                    # read back from the device: the only host synchronisation of the step)
-                    self.cbca_modes[i] = _pf.cbca_auto_mode(self.arms[i]) if self.cbca_mode == _pf.CBCA_AUTO else self.cbca_mode
+                for fn in self._arms_fns:
+                    fn()
             return arms
 
         def make_cbca(src, dst, iters):
@@ -174,13 +181,15 @@ class StereoMatcher(object):
         def other(d):
             return self.tmp[0] if d is not self.tmp[0] else self.tmp[1]
 
+        # the cross arms need the images only: they go first, so that the one host read-back of the step (the choice of the
+        # aggregation schedule) happens while the device queue is still empty instead of draining it mid-step
+        if "cbca1" in st or "cbca2" in st:
+            steps.append(("cross_arms", make_arms()))
         if "features" in st:
             steps.append(("features", make_features()))
         cur = self.volA
         if "cost_volume" in st:
             steps.append(("cost_volume", make_cost_volume(cur)))
-        if "cbca1" in st or "cbca2" in st:
-            steps.append(("cross_arms", make_arms()))
         if "cbca1" in st:
             steps.append(("cbca1", make_cbca(self.volA, self.volB, int(hp["cbca_num_iterations1"]))))
             cur = self.volB
@@ -251,6 +260,7 @@ class StereoMatcher(object):
         """NumPy images in, NumPy disparity out: H2D from pinned memory, hot path, D2H, one sync."""
         torch = self.torch
         with_features = "features" in self.stages
+        with_arms = any(name == "cross_arms" for name, _ in self._steps)
         cur = torch.cuda.current_stream()
         if not hasattr(self, "_copy_stream"):
             self._copy_stream = torch.cuda.Stream()
@@ -267,8 +277,15 @@ class StereoMatcher(object):
             cur.wait_event(self._copy_events[i])
             if with_features:
                 self._feature_fns[i]()          # the left image's features run while the right image is staged and copied
+            if with_arms:
+                # the image's cross arms and the read-back that picks the aggregation schedule ride on the copy stream: the
+                # host waits for this image's upload and two small kernels, not for the features queued on the main stream
+                with torch.cuda.stream(self._copy_stream):
+                    self._arms_fns[i]()
+                    self._copy_events[i].record(self._copy_stream)
+                cur.wait_event(self._copy_events[i])
         for name, fn in self._steps:
-            if name != "features":
+            if name != "features" and name != "cross_arms":
                 fn()
         d = self.result
         self.host_out.copy_(d, non_blocking=True)
