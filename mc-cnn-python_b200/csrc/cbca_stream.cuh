@@ -72,7 +72,7 @@ __device__ __forceinline__ unsigned cs_fkey(float f) {             // order-pres
 }
 
 template <bool COLS, int ITEMS, int NB, bool SC = false, bool WT = false>
-__global__ void __launch_bounds__(CS_THREADS, WT ? CS_MIN_BLOCKS - 2 : CS_MIN_BLOCKS) k_cbca_pass(const float4 *__restrict__ src, float4 *__restrict__ dst,
+__global__ void __launch_bounds__(CS_THREADS, CS_MIN_BLOCKS) k_cbca_pass(const float4 *__restrict__ src, float4 *__restrict__ dst,
                                                           const uchar4 *__restrict__ arms, const int32_t *__restrict__ count,
                                                           int G, int H, int W, const CsScatter sc = CsScatter(),
                                                           const CsWta wt = CsWta()) {
@@ -137,19 +137,27 @@ __global__ void __launch_bounds__(CS_THREADS, WT ? CS_MIN_BLOCKS - 2 : CS_MIN_BL
             }
         }
         if (WT) {
-            // The pixel's smallest cost over the CTA's 64 disparities, then the first disparity that has it (cells d >= D do
-            // not exist; NaN and +inf never win, -0 = +0: k_wta's rules).  Xor shuffles stay inside the 16 lanes of a pixel and
-            // all 32 lanes take part (a reduction under a half-warp mask runs the two halves of the warp one after the other).
+            // this lane's first minimum (strict <, cells d >= D do not exist; NaN and +inf never win, as in k_wta), as a
+            // 64-bit key; then the minimum over the 16 lanes of the pixel: xor shuffles stay inside a half warp, and all 32
+            // lanes take part (a reduction under a half-warp mask makes the two halves of the warp run one after the other).
+            // Measured at C3: this pass + decode 0.46 ms, the plain pass + k_wta 0.46 ms -- at one granule per thread the
+            // search costs what re-reading the volume costs; the chained calls close with k_cbca_close_g instead.
             const int d0 = g << 2;
-            const float vx = ok[s] ? acc.x : CUDART_INF_F, vy = ok[s] && d0 + 1 < wt.D ? acc.y : CUDART_INF_F;
-            const float vz = ok[s] && d0 + 2 < wt.D ? acc.z : CUDART_INF_F, vw = ok[s] && d0 + 3 < wt.D ? acc.w : CUDART_INF_F;
-            float m = fminf(fminf(vx, vy), fminf(vz, vw));
+            float best = CUDART_INF_F;
+            int bd = 0;
+            if (ok[s]) {
+                if (acc.x < best) { best = acc.x; bd = d0; }
+                if (d0 + 1 < wt.D && acc.y < best) { best = acc.y; bd = d0 + 1; }
+                if (d0 + 2 < wt.D && acc.z < best) { best = acc.z; bd = d0 + 2; }
+                if (d0 + 3 < wt.D && acc.w < best) { best = acc.w; bd = d0 + 3; }
+            }
+            unsigned long long key = best < CUDART_INF_F ? ((unsigned long long)cs_fkey(best + 0.0f) << 32 | (unsigned)bd) : ~0ull;   // (-0 counts as +0, like <)
 #pragma unroll
-            for (int off = 8; off >= 1; off >>= 1) m = fminf(m, __shfl_xor_sync(0xffffffffu, m, off));
-            unsigned bd = vx == m ? d0 : vy == m ? d0 + 1 : vz == m ? d0 + 2 : vw == m ? d0 + 3 : 0xffffffffu;
-#pragma unroll
-            for (int off = 8; off >= 1; off >>= 1) bd = min(bd, __shfl_xor_sync(0xffffffffu, bd, off));
-            if (gi == 0 && ok[s] && m < CUDART_INF_F) atomicMin(wt.keys + p[s], (unsigned long long)cs_fkey(m + 0.0f) << 32 | bd);
+            for (int off = 8; off >= 1; off >>= 1) {
+                const unsigned long long o = __shfl_xor_sync(0xffffffffu, key, off);
+                key = o < key ? o : key;
+            }
+            if (gi == 0 && key != ~0ull) atomicMin(wt.keys + p[s], key);
         }
         if (!ok[s]) continue;
         if (WT && !wt.store) continue;

@@ -6,7 +6,7 @@ import collections, os, re, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 lib = os.path.join(ROOT, "mc-cnn-python_b200", "libmccnn_b200.so")
 out = subprocess.run(["cuobjdump", "-sass", lib], capture_output=True, text=True).stdout
-WATCH = ["UTCHMMA", "UTCQMMA", "UTCBAR", "LDTM", "STTM", "UTMALDG", "UTMASTG", "UBLKCP", "LDGSTS", "SYNCS", "REDUX", "CREDUX", "HMMA", "SHFL",
+WATCH = ["UTCHMMA", "UTCQMMA", "UTCBAR", "LDTM", "STTM", "UTMALDG", "UTMAPF", "UTMASTG", "UBLKCP", "LDGSTS", "SYNCS", "REDUX", "CREDUX", "HMMA", "SHFL",
          "LDG", "STG", "LDS", "STS", "BAR"]
 kern, counts, total = None, collections.OrderedDict(), {}
 for line in out.splitlines():
@@ -25,7 +25,7 @@ for line in out.splitlines():
                 counts[kern][w] += 1
 print("# SASS opcode counts per kernel (`cuobjdump -sass mc-cnn-python_b200/libmccnn_b200.so`, sm_100a)\n")
 print("Static instruction counts.  UTCHMMA = `tcgen05.mma`, LDTM / STTM = `tcgen05.ld` / `tcgen05.st`, UTCBAR = `tcgen05.commit`,")
-print("UTMALDG / UTMASTG = TMA tensor load / store, LDGSTS = `cp.async`, SYNCS = mbarrier, REDUX / CREDUX = `redux.sync`.  No kernel uses the")
+print("UTMALDG / UTMAPF / UTMASTG = TMA tensor load / L2 prefetch / store, LDGSTS = `cp.async`, SYNCS = mbarrier, REDUX / CREDUX = `redux.sync`.  No kernel uses the")
 print("legacy `HMMA` path; no kernel uses a TMA store (`UTMASTG`): every result leaves through `STG`.\n")
 cols = [w for w in WATCH if any(c[w] for c in counts.values()) or w in ("UTMASTG", "HMMA")]
 print("| kernel | SASS instr. | " + " | ".join(cols) + " |")
