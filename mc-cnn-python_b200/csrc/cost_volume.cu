@@ -29,7 +29,11 @@
 //          those 32 lines as whole 128-byte lines (8 lanes x float4 per line).  Every L sector is written once, whole.
 //       Round 1 formed S^T as well and wrote both volumes the R way (0.575 ms); staging R through shared memory too
 //       (scripts/experiments/cost_volume_staged.cu) makes every store a whole sector but costs eight times the
-//       instructions (0.72 ms): the epilogue becomes issue bound.  This mix measures 0.52 ms.
+//       instructions (0.72 ms): the epilogue becomes issue bound.  With L in whole sectors the stores stopped being the
+//       bound: three right-chunk stages (a chunk is asked for two chunks ahead, so its flight from L2 overlaps the split
+//       and the MMAs before it) took the kernel from 0.52 to 0.46 ms; what is left is the operand fetch itself (every
+//       right pixel is read by 2.5 left tiles: 0.94 GB of L2 -> SM traffic per call, 0.21 ms with everything else knocked
+//       out) plus MMAs and split that do not fully overlap it.  This mix measures 0.52 ms.
 // k_cost_fill then overwrites the cells that have no correspondent.
 #include "tc_common.cuh"
 
@@ -43,6 +47,7 @@ constexpr int CV_KB_BYTES = CV_BN * 128;   // one K block of a right chunk
 constexpr int CV_A_BYTES = 2 * CV_KA_BYTES, CV_B_BYTES = 2 * CV_KB_BYTES;
 constexpr int CV_THREADS = 512;            // warp 0: MMA issue, warp 1: TMA, warps 2-7: operand split, 8-11: R, 12-15: L
 constexpr int CV_NSPLIT = 192;             // splitter threads (warps 2-7)
+constexpr int CV_NSTAGE = 3;                // right-chunk stages in shared memory
 constexpr int CV_NACC = 4;                 // TMEM accumulators (64 columns each)
 constexpr int CV_TMEM_COLS = CV_NACC * CV_BN;
 constexpr int CV_RING = 64;                // floats per pixel in an L warp's ring (two lines)
@@ -50,9 +55,9 @@ constexpr int CV_RING = 64;                // floats per pixel in an L warp's ri
 struct __align__(1024) CvSmem {
     unsigned char a_hi[CV_A_BYTES], a_lo[CV_A_BYTES];                  // left tile, split
     unsigned char a_raw[CV_A_BYTES];                                   // next left tile as loaded (prefetch)
-    unsigned char b_hi[2][CV_B_BYTES], b_lo[2][CV_B_BYTES];            // right chunks, split, double buffered
+    unsigned char b_hi[CV_NSTAGE][CV_B_BYTES], b_lo[CV_NSTAGE][CV_B_BYTES];   // right chunks (landed raw in b_hi, split in place)
     float l_ring[4][32 * CV_RING];                                     // per L warp: [pixel (lane)][d mod 64]
-    unsigned long long bar_tma_a, bar_tma_b[2], bar_full[CV_NACC], bar_empty[CV_NACC];
+    unsigned long long bar_tma_a, bar_tma_b[CV_NSTAGE], bar_full[CV_NACC], bar_empty[CV_NACC];
     unsigned tmem_base;
 };
 static_assert(sizeof(CvSmem) <= 232448, "shared memory of k_cost_volume_tc");
@@ -128,8 +133,7 @@ k_cost_volume_tc(const __grid_constant__ CvMaps maps, float *__restrict__ L, flo
     }
     if (tid == 32) {
         tc_mbar_init(&sm.bar_tma_a, 1);
-        tc_mbar_init(&sm.bar_tma_b[0], 1);
-        tc_mbar_init(&sm.bar_tma_b[1], 1);
+        for (int i = 0; i < CV_NSTAGE; i++) tc_mbar_init(&sm.bar_tma_b[i], 1);
         for (int i = 0; i < CV_NACC; i++) {
             tc_mbar_init(&sm.bar_full[i], 1);
             tc_mbar_init(&sm.bar_empty[i], 256);
@@ -143,7 +147,7 @@ k_cost_volume_tc(const __grid_constant__ CvMaps maps, float *__restrict__ L, flo
     // instruction descriptor: D = F32, A = B = TF32, A negated (pf:111-112), both K-major, N = 64, M = 128
     const unsigned idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 13) | ((unsigned)(CV_BN >> 3) << 17) |
                            ((unsigned)(CV_BM >> 4) << 24);
-    // chunk g of this CTA uses right-chunk stage g & 1 and accumulator g % CV_NACC; bar_full[g % CV_NACC] completes its
+    // chunk g of this CTA uses right-chunk stage g % CV_NSTAGE and accumulator g % CV_NACC; bar_full[g % CV_NACC] completes its
     // phase (g / CV_NACC) & 1 when the MMAs of chunk g are done (they have then also finished reading the stage)
 
     if (warp == 1) {
@@ -152,10 +156,11 @@ k_cost_volume_tc(const __grid_constant__ CvMaps maps, float *__restrict__ L, flo
             auto issue_b = [&](int tile, int c, unsigned g) {
                 const int h = tile / nwt, w0 = (tile - h * nwt) * CV_BM;
                 const int x0c = w0 + CV_BM - CV_BN * nchunks + CV_BN * c;
-                unsigned char *dst = sm.b_hi[g & 1];
-                tc_mbar_expect_tx(&sm.bar_tma_b[g & 1], CV_B_BYTES);
-                tc_tma_load_3d(dst, &maps.fr, 0, x0c - dbase, h, &sm.bar_tma_b[g & 1]);
-                tc_tma_load_3d(dst + CV_KB_BYTES, &maps.fr, 32, x0c - dbase, h, &sm.bar_tma_b[g & 1]);
+                const unsigned st = g % CV_NSTAGE;
+                unsigned char *dst = sm.b_hi[st];
+                tc_mbar_expect_tx(&sm.bar_tma_b[st], CV_B_BYTES);
+                tc_tma_load_3d(dst, &maps.fr, 0, x0c - dbase, h, &sm.bar_tma_b[st]);
+                tc_tma_load_3d(dst + CV_KB_BYTES, &maps.fr, 32, x0c - dbase, h, &sm.bar_tma_b[st]);
             };
             auto issue_a = [&](int tile) {
                 const int h = tile / nwt, w0 = (tile - h * nwt) * CV_BM;
@@ -163,24 +168,31 @@ k_cost_volume_tc(const __grid_constant__ CvMaps maps, float *__restrict__ L, flo
                 tc_tma_load_3d(sm.a_raw, &maps.fl, 0, w0, h, &sm.bar_tma_a);
                 tc_tma_load_3d(sm.a_raw + CV_KA_BYTES, &maps.fl, 32, w0, h, &sm.bar_tma_a);
             };
+            // the chunk to ask for next: CV_NSTAGE - 1 chunks ahead of the one whose MMAs are awaited, so that a chunk's
+            // flight from L2 overlaps the split and the MMAs of the chunks before it (with two stages a chunk could only be
+            // asked for when the splitters were already waiting for it: its whole latency was exposed, every chunk)
+            int it = blockIdx.x, ic = 0;
+            unsigned ik = 0;
+            auto issue_next = [&]() {
+                if (it >= ntiles) return;
+                issue_b(it, ic, ik);
+                ik++;
+                if (++ic == nchunks) { ic = 0; it += gridDim.x; }
+            };
+            if ((int)blockIdx.x < ntiles) issue_a(blockIdx.x);
+            for (int i = 0; i < CV_NSTAGE; i++) issue_next();
             unsigned g = 0;
-            if ((int)blockIdx.x < ntiles) {
-                issue_a(blockIdx.x);
-                issue_b(blockIdx.x, 0, 0);
-            }
             for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
                 for (int c = 0; c < nchunks; c++, g++) {
-                    // chunk g+1 lands in the stage chunk g-1 used: wait until the MMAs of g-1 are done with it.
-                    if (g > 0) {
-                        tc_mbar_wait_sleep(&sm.bar_full[(g - 1) % CV_NACC], ((g - 1) / CV_NACC) & 1);
-                        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
-                        // chunk g-1 opened a tile <=> c == 1 (or nchunks == 1): its split has consumed a_raw
-                        const bool opened = (nchunks == 1) ? true : (c == 1);
-                        const int opened_tile = (nchunks == 1) ? tile - (int)gridDim.x : tile;
-                        if (opened && opened_tile + (int)gridDim.x < ntiles) issue_a(opened_tile + gridDim.x);
-                    }
-                    if (c + 1 < nchunks) issue_b(tile, c + 1, g + 1);
-                    else if (tile + (int)gridDim.x < ntiles) issue_b(tile + gridDim.x, 0, g + 1);
+                    if (g == 0) continue;
+                    // the MMAs of chunk g-1 are done with its stage: chunk g-1 + CV_NSTAGE lands there
+                    tc_mbar_wait_sleep(&sm.bar_full[(g - 1) % CV_NACC], ((g - 1) / CV_NACC) & 1);
+                    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+                    // chunk g-1 opened a tile <=> c == 1 (or nchunks == 1): its split has consumed a_raw
+                    const bool opened = (nchunks == 1) ? true : (c == 1);
+                    const int opened_tile = (nchunks == 1) ? tile - (int)gridDim.x : tile;
+                    if (opened && opened_tile + (int)gridDim.x < ntiles) issue_a(opened_tile + gridDim.x);
+                    issue_next();
                 }
             }
         }
@@ -189,7 +201,7 @@ k_cost_volume_tc(const __grid_constant__ CvMaps maps, float *__restrict__ L, flo
         unsigned g = 0, ta = 0;
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ta++) {
             for (int c = 0; c < nchunks; c++, g++) {
-                const unsigned stage = g & 1, acc_i = g % CV_NACC;
+                const unsigned stage = g % CV_NSTAGE, acc_i = g % CV_NACC;
                 if (warp >= 2) {
                     if (c == 0) {
                         // the previous tile's MMAs no longer read a_hi / a_lo; the new tile was prefetched into a_raw
@@ -197,7 +209,7 @@ k_cost_volume_tc(const __grid_constant__ CvMaps maps, float *__restrict__ L, flo
                         tc_mbar_wait(&sm.bar_tma_a, ta & 1);
                         tc_split(sm.a_raw, sm.a_hi, sm.a_lo, CV_A_BYTES, tid - 64, CV_NSPLIT);
                     }
-                    tc_mbar_wait(&sm.bar_tma_b[stage], (g >> 1) & 1);
+                    tc_mbar_wait(&sm.bar_tma_b[stage], (g / CV_NSTAGE) & 1);
                     tc_split(sm.b_hi[stage], sm.b_hi[stage], sm.b_lo[stage], CV_B_BYTES, tid - 64, CV_NSPLIT);
                     asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");   // operand accesses -> async proxy
                 }
