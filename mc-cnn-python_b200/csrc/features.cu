@@ -6,6 +6,8 @@
 // k_conv1 (1 -> 64) is a bandwidth-bound float32 SIMT kernel.  Layers 2..n (64 -> 64, 99.8 % of the
 // flops) run on the tensor cores as implicit GEMMs, k_conv64_tc below; plain TF32/BF16 would break the
 // 1e-4 cost-volume tolerance, so operands are split into tf32 hi + lo and three products are accumulated.
+#include <cuda_fp16.h>
+#include <stdlib.h>
 #include "tc_common.cuh"
 
 namespace mccnn {
@@ -314,6 +316,279 @@ k_conv64_tc(const __grid_constant__ CtcMaps maps, const float *__restrict__ bias
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"(512) : "memory");
 }
 
+// ------------------------------------------------------------------------------------------
+// The same kernel with FP16 operands (k_conv64_h).  hi = fp16(x) and lo = fp16(x - hi) carry the same 11 + 11
+// significant bits as the TF32 split, so hi.hi + hi.lo + lo.hi in float32 has the same accuracy, but kind::f16 MMAs
+// take K = 16 per instruction: half as many MMAs for the same contraction.  A 32-channel block is a 64-byte row
+// (SWIZZLE_64B); the weights of BOTH channel blocks fit in shared memory at once (144 KB) and are loaded once per CTA
+// instead of once per tile and block.  Range: fp16 overflows at 65504 -- activations of a trained MC-CNN are O(1..10);
+// mccnn_features keeps the TF32 kernel behind MCCNN_CONV_TF32=1 for networks outside that range.  Values below 6e-5
+// lose relative (not absolute) precision in the lo part: an absolute error of 3e-8 per operand, far below the 2e-5 gate.
+// ------------------------------------------------------------------------------------------
+constexpr int CH_TILE_BYTES = 128 * 64;         // fp16 operand tile of one input row: 128 pixels x 32 channels, 64B-swizzled
+constexpr int CH_WBLK_BYTES = 64 * 64;          // one weight block: 64 output maps x 32 input channels, fp16
+constexpr int CH_W_BYTES = 2 * 9 * 2 * CH_WBLK_BYTES;   // both channel blocks, nine taps, hi and lo: 144 KB
+
+struct __align__(1024) ChSmem {
+    unsigned char w[2][2][3][3][CH_WBLK_BYTES];  // [channel block][hi, lo][kx][2 - ky]
+    unsigned char raw[2][CT_ROW_BYTES];          // input rows as loaded (float32, 128B-swizzled)
+    unsigned char a_hi[2][CH_TILE_BYTES], a_lo[2][CH_TILE_BYTES];
+    unsigned long long bar_w, bar_row[2], bar_rowdone[2], bar_full[2], bar_empty[2], bar_zero;
+    unsigned tmem_base;
+};
+
+// K-major, 64B-swizzled operand: rows of 64 bytes, 8-row groups 512 bytes apart
+__device__ __forceinline__ unsigned long long ch_smem_desc(unsigned smem_addr) {
+    unsigned long long d = 0;
+    d |= (unsigned long long)((smem_addr >> 4) & 0x3fff);
+    d |= (unsigned long long)1 << 16;
+    d |= (unsigned long long)(512 >> 4) << 32;
+    d |= (unsigned long long)1 << 46;
+    d |= (unsigned long long)4 << 61;                     // SWIZZLE_64B
+    return d;
+}
+__device__ __forceinline__ void ch_mma_f16(unsigned tmem_d, unsigned long long a_desc, unsigned long long b_desc, unsigned idesc,
+                                           unsigned accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// raw: [128 pixels][32 channels] float32 with the 128B swizzle of the TMA load (16-byte chunk c of pixel p sits at chunk
+// c ^ (p & 7)); hi / lo: [128 pixels][32 channels] fp16 with the 64B swizzle (chunk c at c ^ ((p >> 1) & 3))
+__device__ __forceinline__ void ch_split(const unsigned char *raw, unsigned char *hi, unsigned char *lo, int ftid, int nthr) {
+    const float4 *r4 = reinterpret_cast<const float4 *>(raw);
+#pragma unroll 2
+    for (int i = ftid; i < CT_ROW_BYTES / 16; i += nthr) {
+        const int p = i >> 3, cg = (i & 7) ^ (p & 7);            // pixel, channel group (4 channels)
+        const float4 x = r4[i];
+        const __half2 h01 = __floats2half2_rn(x.x, x.y), h23 = __floats2half2_rn(x.z, x.w);
+        const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+        const __half2 l01 = __floats2half2_rn(x.x - f01.x, x.y - f01.y), l23 = __floats2half2_rn(x.z - f23.x, x.w - f23.y);
+        const int off = p * 64 + ((((cg >> 1) ^ ((p >> 1) & 3))) << 4) + ((cg & 1) << 3);
+        *reinterpret_cast<uint2 *>(hi + off) = make_uint2(*reinterpret_cast<const unsigned *>(&h01), *reinterpret_cast<const unsigned *>(&h23));
+        *reinterpret_cast<uint2 *>(lo + off) = make_uint2(*reinterpret_cast<const unsigned *>(&l01), *reinterpret_cast<const unsigned *>(&l23));
+    }
+}
+
+// HWIO [3][3][ic][oc] float32 -> [tap][oc][ic] fp16, hi = fp16(w) and lo = fp16(w - hi)
+__global__ void k_conv_prep_weights_h(const float *__restrict__ w, __half *__restrict__ whi, __half *__restrict__ wlo) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;        // index into [tap][oc][ic]
+    if (i >= 9 * F * F) return;
+    const int ic = i % F, oc = (i / F) % F, tap = i / (F * F);
+    const float x = w[((size_t)tap * F + ic) * F + oc];
+    const __half h = __float2half_rn(x);
+    whi[i] = h;
+    wlo[i] = __float2half_rn(x - __half2float(h));
+}
+
+template <bool LAST>
+__global__ void __launch_bounds__(CT_THREADS, 1)
+k_conv64_h(const __grid_constant__ CtcMaps maps, const float *__restrict__ bias, float *__restrict__ out, int OH, int OW,
+            int ntx, int ntiles) {
+    extern __shared__ __align__(1024) unsigned char ctc_raw[];
+    ChSmem &sm = *reinterpret_cast<ChSmem *>(ctc_raw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(tc_smem_u32(&sm.tmem_base)),
+                     "r"(512)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+    }
+    if (tid == 32) {
+        tc_mbar_init(&sm.bar_w, 1);
+        tc_mbar_init(&sm.bar_zero, 1);
+        for (int i = 0; i < 2; i++) {
+            tc_mbar_init(&sm.bar_row[i], 1);
+            tc_mbar_init(&sm.bar_rowdone[i], 1);
+            tc_mbar_init(&sm.bar_full[i], 1);
+            tc_mbar_init(&sm.bar_empty[i], 256);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+    const unsigned tmem_base = sm.tmem_base;
+    // instruction descriptor: D = F32, A = B = F16, both K-major, M = 128; N (64, 128 or 192) is filled in per MMA
+    const unsigned idesc_base = (1u << 4) | ((unsigned)(128 >> 4) << 24);
+    constexpr int NROW = CT_ROWS + 2;           // input rows per tile
+
+    // A CTA takes its tiles two at a time (one per accumulator buffer) and visits  block 0 of both, then block 1 of both:
+    // the weights are reloaded once per tile on average, and EVERY tile accumulates block 0 before block 1 -- a pixel's
+    // features do not depend on where its tile falls in some CTA's sequence, so a row band of an image (slab.py) gives
+    // the bits of the whole image.  Row steps are numbered globally in that order.
+    if (warp == 1) {
+        // ================= TMA producer (one lane) =================
+        if (lane == 0) {
+            unsigned rr = 0;
+            // the weights of both channel blocks, all nine taps, hi and lo (144 KB as fp16) stay for the whole kernel
+            tc_mbar_expect_tx(&sm.bar_w, CH_W_BYTES);
+            for (int kb = 0; kb < 2; kb++)
+                for (int tap = 0; tap < 9; tap++) {
+                    tc_tma_load_3d(sm.w[kb][0][tap % 3][2 - tap / 3], &maps.whi, kb * 32, 0, tap, &sm.bar_w);
+                    tc_tma_load_3d(sm.w[kb][1][tap % 3][2 - tap / 3], &maps.wlo, kb * 32, 0, tap, &sm.bar_w);
+                }
+            for (int tile0 = blockIdx.x; tile0 < ntiles; tile0 += 2 * gridDim.x) {
+              for (int kb = 0; kb < 2; kb++) {
+                for (int mem = 0; mem < 2; mem++) {
+                    const int tile = tile0 + mem * gridDim.x;
+                    if (tile >= ntiles) break;
+                    const int ty = tile / ntx, y0 = ty * CT_ROWS, x0 = (tile - ty * ntx) * CT_PIX;
+                    for (int r = 0; r < NROW; r++, rr++) {
+                        // the row buffer was last used by step rr - 2
+                        if (rr >= 2) {
+                            tc_mbar_wait_sleep(&sm.bar_rowdone[rr & 1], ((rr - 2) >> 1) & 1);
+                            asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+                        }
+                        tc_mbar_expect_tx(&sm.bar_row[rr & 1], CT_ROW_BYTES);
+                        tc_tma_load_3d(sm.raw[rr & 1], &maps.in, kb * 32, x0, y0 + r, &sm.bar_row[rr & 1]);
+                    }
+                }
+              }
+            }
+        }
+    } else if (warp < 8) {
+        // ================= operand split (warps 2-7) and MMA issue (warp 0, lane 0) =================
+        unsigned rr = 0, pair = 0;
+        for (int tile0 = blockIdx.x; tile0 < ntiles; tile0 += 2 * gridDim.x, pair++) {
+          for (int kb = 0; kb < 2; kb++) {
+            for (int mem = 0; mem < 2; mem++) {
+                if (tile0 + mem * (int)gridDim.x >= ntiles) break;
+                const unsigned abuf = mem, tt = 2 * pair + mem;
+                const int bi = kb;
+                for (int r = 0; r < NROW; r++, rr++) {
+                    const unsigned rb = rr & 1;
+                    if (warp >= 2) {
+                        tc_mbar_wait(&sm.bar_row[rb], (rr >> 1) & 1);
+                        ch_split(sm.raw[rb], sm.a_hi[rb], sm.a_lo[rb], tid - 64, CT_NSPLIT);
+                        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+                    }
+                    tc_named_barrier(1, 32 + CT_NSPLIT);
+                    if (tid == 0) {
+                        if (rr == 0) tc_mbar_wait(&sm.bar_w, 0);
+                        if (bi == 0 && r == 0 && tt >= 2) tc_mbar_wait(&sm.bar_empty[abuf], ((tt >> 1) - 1) & 1);
+                        if (rr == 0) tc_mbar_wait(&sm.bar_zero, 0);
+                        asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+                        const unsigned long long ah = ch_smem_desc(tc_smem_u32(sm.a_hi[rb])), al = ch_smem_desc(tc_smem_u32(sm.a_lo[rb]));
+                        // Input row r feeds accumulator j = r - ky for every kernel row ky it can pair with: the weights
+                        // of those kernel rows are stacked (ky descending = j ascending), so ONE MMA with N = 64, 128 or
+                        // 192 updates the adjacent accumulators j = r - kymax .. r - kymin.  Accumulators start from the
+                        // zeros the epilogue leaves in TMEM, so every MMA accumulates.
+                        const int kymax = min(2, r), kymin = max(0, r - (CT_ROWS - 1));
+                        const unsigned nacc = (unsigned)(kymax - kymin + 1);
+                        const unsigned idesc_n = idesc_base | ((nacc * F >> 3) << 17);
+                        const unsigned d_tmem = tmem_base + abuf * (CT_ROWS * F) + (unsigned)(r - kymax) * F;
+#pragma unroll
+                        for (int kx = 0; kx < 3; kx++) {
+                            const unsigned long long wh = ch_smem_desc(tc_smem_u32(sm.w[bi][0][kx][2 - kymax]));
+                            const unsigned long long wl = ch_smem_desc(tc_smem_u32(sm.w[bi][1][kx][2 - kymax]));
+#pragma unroll
+                            for (int ks = 0; ks < 2; ks++) {                       // K = 16 halves = 32 bytes per MMA
+                                const unsigned long long aoff = (unsigned long long)((kx * 64 + ks * 32) >> 4);
+                                const unsigned long long woff = (unsigned long long)((ks * 32) >> 4);
+                                ch_mma_f16(d_tmem, ah + aoff, wh + woff, idesc_n, 1);
+                                ch_mma_f16(d_tmem, ah + aoff, wl + woff, idesc_n, 1);
+                                ch_mma_f16(d_tmem, al + aoff, wh + woff, idesc_n, 1);
+                            }
+                        }
+                        tc_mma_commit(&sm.bar_rowdone[rb]);
+                        if (bi == 1 && r == NROW - 1) tc_mma_commit(&sm.bar_full[abuf]);
+                    }
+                }
+            }
+          }
+        }
+    } else {
+        // ================= epilogue (warps 8-15): two warps per TMEM lane quarter, two output rows each =================
+        const int q = warp & 3, half = (warp - 8) >> 2;
+        const int m = 32 * q + lane;
+        const float4 *b4 = reinterpret_cast<const float4 *>(bias);
+        // MMAs only ever accumulate: this warp's share of both accumulator buffers (its lane quarter, its two rows)
+        // starts as zeros and is zeroed again after every read
+        auto zero_acc = [&](unsigned abuf, int j) {
+            const unsigned taddr = tmem_base + ((unsigned)(32 * q) << 16) + abuf * (CT_ROWS * F) + j * F;
+            tc_tmem_st32_zero(taddr);
+            tc_tmem_st32_zero(taddr + 32);
+        };
+        for (unsigned ab = 0; ab < 2; ab++)
+            for (int jj = 0; jj < CT_ROWS / 2; jj++) zero_acc(ab, half * (CT_ROWS / 2) + jj);
+        asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+        tc_named_barrier(2, 256);                       // all eight epilogue warps have zeroed their part ...
+        if (tid == 256) tc_mbar_arrive(&sm.bar_zero);    // ... tell the MMA issuer
+        unsigned tt = 0;
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, tt++) {
+            const unsigned abuf = tt & 1;
+            const int ty = tile / ntx, y0 = ty * CT_ROWS, x0 = (tile - ty * ntx) * CT_PIX;
+            tc_mbar_wait(&sm.bar_full[abuf], (tt >> 1) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+#pragma unroll 1
+            for (int jj = 0; jj < CT_ROWS / 2; jj++) {
+                const int j = half * (CT_ROWS / 2) + jj;
+                const int y = y0 + j, x = x0 + m;
+                unsigned v0[32], v1[32];
+                const unsigned taddr = tmem_base + ((unsigned)(32 * q) << 16) + abuf * (CT_ROWS * F) + j * F;
+                tc_tmem_ld32(taddr, v0);
+                tc_tmem_ld32(taddr + 32, v1);
+                zero_acc(abuf, j);
+                float ss = 0.f;
+#pragma unroll
+                for (int o = 0; o < 32; o += 4) {
+                    const float4 ba = __ldg(b4 + (o >> 2)), bb = __ldg(b4 + 8 + (o >> 2));
+                    float t;
+                    t = __uint_as_float(v0[o]) + ba.x;     v0[o] = __float_as_uint(t);     ss = fmaf(t, t, ss);
+                    t = __uint_as_float(v0[o + 1]) + ba.y; v0[o + 1] = __float_as_uint(t); ss = fmaf(t, t, ss);
+                    t = __uint_as_float(v0[o + 2]) + ba.z; v0[o + 2] = __float_as_uint(t); ss = fmaf(t, t, ss);
+                    t = __uint_as_float(v0[o + 3]) + ba.w; v0[o + 3] = __float_as_uint(t); ss = fmaf(t, t, ss);
+                    t = __uint_as_float(v1[o]) + bb.x;     v1[o] = __float_as_uint(t);     ss = fmaf(t, t, ss);
+                    t = __uint_as_float(v1[o + 1]) + bb.y; v1[o + 1] = __float_as_uint(t); ss = fmaf(t, t, ss);
+                    t = __uint_as_float(v1[o + 2]) + bb.z; v1[o + 2] = __float_as_uint(t); ss = fmaf(t, t, ss);
+                    t = __uint_as_float(v1[o + 3]) + bb.w; v1[o + 3] = __float_as_uint(t); ss = fmaf(t, t, ss);
+                }
+                const float inv = LAST ? 1.0f / sqrtf(fmaxf(ss, 1e-12f)) : 1.0f;   // model.py:64
+                if (y < OH && m < CT_PIX && x < OW) {
+                    float *dst = out + ((size_t)y * OW + x) * F;
+#pragma unroll
+                    for (int o = 0; o < 32; o += 8) {
+                        float e[8];
+#pragma unroll
+                        for (int k = 0; k < 8; k++) {
+                            const float t = __uint_as_float(v0[o + k]);
+                            e[k] = LAST ? t * inv : fmaxf(t, 0.f);                  // model.py:120-123
+                        }
+                        asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(dst + o), "f"(e[0]), "f"(e[1]),
+                                     "f"(e[2]), "f"(e[3]), "f"(e[4]), "f"(e[5]), "f"(e[6]), "f"(e[7])
+                                     : "memory");
+                    }
+#pragma unroll
+                    for (int o = 0; o < 32; o += 8) {
+                        float e[8];
+#pragma unroll
+                        for (int k = 0; k < 8; k++) {
+                            const float t = __uint_as_float(v1[o + k]);
+                            e[k] = LAST ? t * inv : fmaxf(t, 0.f);
+                        }
+                        asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(dst + 32 + o), "f"(e[0]), "f"(e[1]),
+                                     "f"(e[2]), "f"(e[3]), "f"(e[4]), "f"(e[5]), "f"(e[6]), "f"(e[7])
+                                     : "memory");
+                    }
+                }
+            }
+            asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");
+            asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+            tc_mbar_arrive(&sm.bar_empty[abuf]);
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"(512) : "memory");
+}
+
 // Single-layer network (num_layers == 1): normalise the conv1 output in place.
 __global__ void k_l2norm64(float *__restrict__ x, long long P) {
     long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -336,6 +611,14 @@ using namespace mccnn;
 
 extern "C" {
 
+// operand format of layers 2..n: fp16 hi/lo (default) or the TF32 split (MCCNN_CONV_TF32=1: networks whose activations
+// leave fp16's range); read once, mccnn_features_prepare and the forward calls must agree
+static bool conv_tf32() {
+    static int v = -1;
+    if (v < 0) { const char *e = getenv("MCCNN_CONV_TF32"); v = (e && atoi(e) != 0) ? 1 : 0; }
+    return v == 1;
+}
+
 static size_t conv_weights_floats(int num_layers) { return (size_t)(num_layers > 1 ? num_layers - 1 : 0) * 2 * 9 * F * F; }
 
 size_t mccnn_features_scratch_bytes(int H, int W, int pad, int num_layers) {
@@ -354,7 +637,12 @@ int mccnn_features_prepare(int num_layers, const float *const *weights_host, voi
     MCCNN_REQUIRE(num_layers == 1 || (prepared && ((uintptr_t)prepared & 31) == 0), "features_prepare: prepared must be 32-byte aligned");
     for (int l = 1; l < num_layers; l++) {
         float *whi = (float *)prepared + (size_t)(l - 1) * 2 * 9 * F * F, *wlo = whi + 9 * F * F;
-        k_conv_prep_weights<<<cdiv(9 * F * F, 256), 256, 0, (cudaStream_t)stream>>>(weights_host[l], whi, wlo);
+        if (conv_tf32()) {
+            k_conv_prep_weights<<<cdiv(9 * F * F, 256), 256, 0, (cudaStream_t)stream>>>(weights_host[l], whi, wlo);
+        } else {
+            __half *hhi = reinterpret_cast<__half *>(whi);
+            k_conv_prep_weights_h<<<cdiv(9 * F * F, 256), 256, 0, (cudaStream_t)stream>>>(weights_host[l], hhi, hhi + 9 * F * F);
+        }
         MCCNN_LAUNCHED("conv_prep_weights");
     }
     return MCCNN_OK;
@@ -396,6 +684,9 @@ static int features_impl(const float *img, int H, int W, int pad, int num_layers
     MCCNN_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
     MCCNN_CUDA(cudaFuncSetAttribute(k_conv64_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CtcSmem)));
     MCCNN_CUDA(cudaFuncSetAttribute(k_conv64_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CtcSmem)));
+    MCCNN_CUDA(cudaFuncSetAttribute(k_conv64_h<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ChSmem)));
+    MCCNN_CUDA(cudaFuncSetAttribute(k_conv64_h<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ChSmem)));
+    const bool tf32 = conv_tf32();
     const float *src = dst;
     int ih = oh, iw = ow;
     for (int l = 1; l < num_layers; l++) {
@@ -403,22 +694,31 @@ static int features_impl(const float *img, int H, int W, int pad, int num_layers
         const bool last = (l == num_layers - 1);
         float *d = last ? out : buf[l & 1];
         float *whi = wsplit + (size_t)(l - 1) * 2 * 9 * F * F, *wlo = whi + 9 * F * F;
+        __half *hhi = reinterpret_cast<__half *>(whi), *hlo = hhi + 9 * F * F;
         if (!prepared) {
-            k_conv_prep_weights<<<cdiv(9 * F * F, 256), 256, 0, s>>>(weights_host[l], whi, wlo);
+            if (tf32) k_conv_prep_weights<<<cdiv(9 * F * F, 256), 256, 0, s>>>(weights_host[l], whi, wlo);
+            else k_conv_prep_weights_h<<<cdiv(9 * F * F, 256), 256, 0, s>>>(weights_host[l], hhi, hlo);
             MCCNN_LAUNCHED("conv_prep_weights");
         }
         CtcMaps maps;
         int rc = tc_encode_map_3d(maps.in, src, F, iw, ih, 32, 128, true, "features");
         if (rc) return rc;
-        rc = tc_encode_map_3d(maps.whi, whi, F, F, 9, 32, F, true, "features");
+        rc = tf32 ? tc_encode_map_3d(maps.whi, whi, F, F, 9, 32, F, true, "features")
+                  : tc_encode_map_3d_f16_sw64(maps.whi, hhi, F, F, 9, 32, F, "features");
         if (rc) return rc;
-        rc = tc_encode_map_3d(maps.wlo, wlo, F, F, 9, 32, F, true, "features");
+        rc = tf32 ? tc_encode_map_3d(maps.wlo, wlo, F, F, 9, 32, F, true, "features")
+                  : tc_encode_map_3d_f16_sw64(maps.wlo, hlo, F, F, 9, 32, F, "features");
         if (rc) return rc;
         const int ntx = cdiv(ow, CT_PIX), nty = cdiv(oh, CT_ROWS);
         const int ntiles = ntx * nty;
         const int grid = ntiles < num_sms ? ntiles : num_sms;
-        if (last) k_conv64_tc<true><<<grid, CT_THREADS, sizeof(CtcSmem), s>>>(maps, biases_host[l], d, oh, ow, ntx, ntiles);
-        else k_conv64_tc<false><<<grid, CT_THREADS, sizeof(CtcSmem), s>>>(maps, biases_host[l], d, oh, ow, ntx, ntiles);
+        if (tf32) {
+            if (last) k_conv64_tc<true><<<grid, CT_THREADS, sizeof(CtcSmem), s>>>(maps, biases_host[l], d, oh, ow, ntx, ntiles);
+            else k_conv64_tc<false><<<grid, CT_THREADS, sizeof(CtcSmem), s>>>(maps, biases_host[l], d, oh, ow, ntx, ntiles);
+        } else {
+            if (last) k_conv64_h<true><<<grid, CT_THREADS, sizeof(ChSmem), s>>>(maps, biases_host[l], d, oh, ow, ntx, ntiles);
+            else k_conv64_h<false><<<grid, CT_THREADS, sizeof(ChSmem), s>>>(maps, biases_host[l], d, oh, ow, ntx, ntiles);
+        }
         MCCNN_LAUNCHED("conv64_tc");
         src = d; ih = oh; iw = ow;
     }

@@ -124,6 +124,10 @@ __device__ __forceinline__ void tc_split(const unsigned char *raw, unsigned char
     }
 }
 
+// fp16 tensor [d2][d1][d0] (d0 contiguous), box {b0, b1, 1}, 64-byte swizzle (b0 * 2 must be 64)
+static inline int tc_encode_map_3d_f16_sw64(CUtensorMap &map, const void *base, unsigned long long d0, unsigned long long d1,
+                                            unsigned long long d2, unsigned b0, unsigned b1, const char *what);
+
 typedef CUresult (*TcEncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                     const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -152,6 +156,29 @@ static inline int tc_encode_map_3d(CUtensorMap &map, const float *base, unsigned
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         set_error("%s: cuTensorMapEncodeTiled failed (%d)", what, (int)r);
+        return MCCNN_ERR_CUDA;
+    }
+    return MCCNN_OK;
+}
+
+static inline int tc_encode_map_3d_f16_sw64(CUtensorMap &map, const void *base, unsigned long long d0, unsigned long long d1,
+                                            unsigned long long d2, unsigned b0, unsigned b1, const char *what) {
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess ||
+        qres != cudaDriverEntryPointSuccess) {
+        set_error("%s: cuTensorMapEncodeTiled is not available from this driver", what);
+        return MCCNN_ERR_CUDA;
+    }
+    const cuuint64_t gdim[3] = {d0, d1, d2};
+    const cuuint64_t gstr[2] = {d0 * 2, d1 * d0 * 2};
+    const cuuint32_t box[3] = {b0, b1, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = ((TcEncodeTiledFn)p)(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void *>(base), gdim, gstr, box, estr,
+                                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("%s: cuTensorMapEncodeTiled (fp16) failed (%d)", what, (int)r);
         return MCCNN_ERR_CUDA;
     }
     return MCCNN_OK;
