@@ -532,7 +532,7 @@ def run_ours(args):
                                "achieved_GBps": gbs, "frac_of_hbm_peak": gbs / peak}
         if "features" in acc:
             fl = 2.0 * H * W * 296064.0
-            kernels["features"] = {"kernel": "k_conv64_tc (tcgen05 tf32 x3)", "ms": acc["features"], "TFLOPs": fl / 1e12,
+            kernels["features"] = {"kernel": "k_conv64_h (tcgen05 kind::f16, fp16 hi/lo x3 products = float32 accuracy)", "ms": acc["features"], "TFLOPs": fl / 1e12,
                                    "achieved_TFLOPps": fl / (acc["features"] * 1e-3) / 1e12}
         # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture
         traffic = {}

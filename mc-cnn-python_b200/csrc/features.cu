@@ -4,8 +4,9 @@
 // but the last (model.py:51-60), and x * rsqrt(max(sum_c x^2, 1e-12)) over channels (model.py:64).
 //
 // k_conv1 (1 -> 64) is a bandwidth-bound float32 SIMT kernel.  Layers 2..n (64 -> 64, 99.8 % of the
-// flops) run on the tensor cores as implicit GEMMs, k_conv64_tc below; plain TF32/BF16 would break the
-// 1e-4 cost-volume tolerance, so operands are split into tf32 hi + lo and three products are accumulated.
+// flops) run on the tensor cores as implicit GEMMs; one TF32/BF16/FP16 product would break the 1e-4 cost-volume
+// tolerance, so operands are split into hi + lo and three products are accumulated in float32:
+// k_conv64_h (default: fp16 hi/lo, kind::f16, half the MMAs) and k_conv64_tc (tf32 hi/lo, MCCNN_CONV_TF32=1).
 #include <cuda_fp16.h>
 #include <stdlib.h>
 #include "tc_common.cuh"

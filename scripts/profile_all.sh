@@ -6,7 +6,7 @@ echo "== launch list (bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-flat-
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/r2f_launches.csv \
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-flat-stage > gpurun_out/ncu_list.log 2>&1
 tail -1 gpurun_out/ncu_list.log | cut -c1-200
-for k in k_cbca_colrow_g k_cbca_close_g k_cbca_pass k_sgm_pass k_conv64_tc; do
+for k in k_cbca_colrow_g k_cbca_close_g k_cbca_pass k_sgm_pass k_conv64_h; do
   timeout 600 ncu --set full --clock-control none --import-source on -k regex:$k -s 4 -c 2 -o gpurun_out/r2f_$k -f python scripts/profile_step.py 2 > gpurun_out/ncu_$k.log 2>&1
   tail -1 gpurun_out/ncu_$k.log
 done
