@@ -329,12 +329,14 @@ k_conv64_tc(const __grid_constant__ CtcMaps maps, const float *__restrict__ bias
 constexpr int CH_TILE_BYTES = 128 * 64;         // fp16 operand tile of one input row: 128 pixels x 32 channels, 64B-swizzled
 constexpr int CH_WBLK_BYTES = 64 * 64;          // one weight block: 64 output maps x 32 input channels, fp16
 constexpr int CH_W_BYTES = 2 * 9 * 2 * CH_WBLK_BYTES;   // both channel blocks, nine taps, hi and lo: 144 KB
+constexpr int CH_NRAW = 3;                      // float32 row buffers
 
 struct __align__(1024) ChSmem {
     unsigned char w[2][2][3][3][CH_WBLK_BYTES];  // [channel block][hi, lo][kx][2 - ky]
-    unsigned char raw[2][CT_ROW_BYTES];          // input rows as loaded (float32, 128B-swizzled)
+    unsigned char raw[CH_NRAW][CT_ROW_BYTES];    // input rows as loaded (float32, 128B-swizzled): a ring of their own, so that
+                                                 // a row can be asked for before the MMAs two steps back have finished
     unsigned char a_hi[2][CH_TILE_BYTES], a_lo[2][CH_TILE_BYTES];
-    unsigned long long bar_w, bar_row[2], bar_rowdone[2], bar_full[2], bar_empty[2], bar_zero;
+    unsigned long long bar_w, bar_row[CH_NRAW], bar_rawfree[CH_NRAW], bar_rowdone[2], bar_full[2], bar_empty[2], bar_zero;
     unsigned tmem_base;
 };
 
@@ -403,8 +405,11 @@ k_conv64_h(const __grid_constant__ CtcMaps maps, const float *__restrict__ bias,
     if (tid == 32) {
         tc_mbar_init(&sm.bar_w, 1);
         tc_mbar_init(&sm.bar_zero, 1);
-        for (int i = 0; i < 2; i++) {
+        for (int i = 0; i < CH_NRAW; i++) {
             tc_mbar_init(&sm.bar_row[i], 1);
+            tc_mbar_init(&sm.bar_rawfree[i], 1);
+        }
+        for (int i = 0; i < 2; i++) {
             tc_mbar_init(&sm.bar_rowdone[i], 1);
             tc_mbar_init(&sm.bar_full[i], 1);
             tc_mbar_init(&sm.bar_empty[i], 256);
@@ -441,13 +446,14 @@ k_conv64_h(const __grid_constant__ CtcMaps maps, const float *__restrict__ bias,
                     if (tile >= ntiles) break;
                     const int ty = tile / ntx, y0 = ty * CT_ROWS, x0 = (tile - ty * ntx) * CT_PIX;
                     for (int r = 0; r < NROW; r++, rr++) {
-                        // the row buffer was last used by step rr - 2
-                        if (rr >= 2) {
-                            tc_mbar_wait_sleep(&sm.bar_rowdone[rr & 1], ((rr - 2) >> 1) & 1);
+                        // the raw buffer was last used by step rr - CH_NRAW: free once that step's split has read it
+                        const unsigned rs = rr % CH_NRAW;
+                        if (rr >= CH_NRAW) {
+                            tc_mbar_wait_sleep(&sm.bar_rawfree[rs], ((rr - CH_NRAW) / CH_NRAW) & 1);
                             asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
                         }
-                        tc_mbar_expect_tx(&sm.bar_row[rr & 1], CT_ROW_BYTES);
-                        tc_tma_load_3d(sm.raw[rr & 1], &maps.in, kb * 32, x0, y0 + r, &sm.bar_row[rr & 1]);
+                        tc_mbar_expect_tx(&sm.bar_row[rs], CT_ROW_BYTES);
+                        tc_tma_load_3d(sm.raw[rs], &maps.in, kb * 32, x0, y0 + r, &sm.bar_row[rs]);
                     }
                 }
               }
@@ -464,13 +470,17 @@ k_conv64_h(const __grid_constant__ CtcMaps maps, const float *__restrict__ bias,
                 const int bi = kb;
                 for (int r = 0; r < NROW; r++, rr++) {
                     const unsigned rb = rr & 1;
+                    const unsigned rs = rr % CH_NRAW;
                     if (warp >= 2) {
-                        tc_mbar_wait(&sm.bar_row[rb], (rr >> 1) & 1);
-                        ch_split(sm.raw[rb], sm.a_hi[rb], sm.a_lo[rb], tid - 64, CT_NSPLIT);
+                        // the fp16 tiles of this step were last read by the MMAs of step rr - 2
+                        if (rr >= 2) tc_mbar_wait(&sm.bar_rowdone[rb], ((rr - 2) >> 1) & 1);
+                        tc_mbar_wait(&sm.bar_row[rs], (rr / CH_NRAW) & 1);
+                        ch_split(sm.raw[rs], sm.a_hi[rb], sm.a_lo[rb], tid - 64, CT_NSPLIT);
                         asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
                     }
                     tc_named_barrier(1, 32 + CT_NSPLIT);
                     if (tid == 0) {
+                        tc_mbar_arrive(&sm.bar_rawfree[rs]);                       // every splitter is done with the raw row
                         if (rr == 0) tc_mbar_wait(&sm.bar_w, 0);
                         if (bi == 0 && r == 0 && tt >= 2) tc_mbar_wait(&sm.bar_empty[abuf], ((tt >> 1) - 1) & 1);
                         if (rr == 0) tc_mbar_wait(&sm.bar_zero, 0);
