@@ -65,7 +65,9 @@ int mccnn_features(const float *img, int H, int W, int pad, int num_layers,
 /* The same with the network's constant part done once (the reference builds its graph once per process and runs it
  * per image, pf:30-47): mccnn_features_prepare writes the hi/lo tf32 split of the weights of layers 2..n into
  * `prepared` (mccnn_features_weights_bytes(num_layers) bytes, 32-byte aligned); mccnn_features_prepared uses it
- * instead of splitting the weights on every call.  Same results bit for bit. */
+ * instead of splitting the weights on every call.  Same results bit for bit.
+ * Layers 2..n run on the tensor cores with FP16 hi/lo operands (three products, float32 accumulation: float32 accuracy);
+ * a layer whose input or weights exceed fp16's range runs with TF32 hi/lo operands instead (device-side decision). */
 size_t mccnn_features_weights_bytes(int num_layers);
 int mccnn_features_prepare(int num_layers, const float *const *weights_host, void *prepared, void *stream);
 int mccnn_features_prepared(const float *img, int H, int W, int pad, int num_layers,

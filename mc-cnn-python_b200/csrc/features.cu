@@ -8,12 +8,14 @@
 // tolerance, so operands are split into hi + lo and three products are accumulated in float32:
 // k_conv64_h (default: fp16 hi/lo, kind::f16, half the MMAs) and k_conv64_tc (tf32 hi/lo, MCCNN_CONV_TF32=1).
 #include <cuda_fp16.h>
+#include <math_constants.h>
 #include <stdlib.h>
 #include "tc_common.cuh"
 
 namespace mccnn {
 
 constexpr int F = 64;              // feature maps (model.py:38)
+constexpr float CONV_F16_MAX = 6.0e4f;   // operands beyond this go through the TF32 kernel (fp16 overflows at 65504)
 
 // Layer 1: 1 -> 64.  A thread owns 4 output channels -- their 36 weights and 4 biases stay in registers -- and
 // walks C1_PX pixels of a row, 16 apart (the 16 channel quads of a pixel are 16 consecutive lanes: every store of a
@@ -21,7 +23,7 @@ constexpr int F = 64;              // feature maps (model.py:38)
 constexpr int C1_PX = 8;
 __global__ void __launch_bounds__(256) k_conv1(const float *__restrict__ img, const float *__restrict__ wgt,
                                                const float *__restrict__ bias, float *__restrict__ out, int H, int W,
-                                               int pad, int OH, int OW, int relu) {
+                                               int pad, int OH, int OW, int relu, int *__restrict__ big) {
     const int oc = (threadIdx.x & 15) * 4, slot = threadIdx.x >> 4, y = blockIdx.y;
     float4 wv[9];
 #pragma unroll
@@ -45,6 +47,8 @@ __global__ void __launch_bounds__(256) k_conv1(const float *__restrict__ img, co
             }
         float4 acc = make_float4(bv.x + sum.x, bv.y + sum.y, bv.z + sum.z, bv.w + sum.w);
         if (relu) { acc.x = fmaxf(acc.x, 0.f); acc.y = fmaxf(acc.y, 0.f); acc.z = fmaxf(acc.z, 0.f); acc.w = fmaxf(acc.w, 0.f); }
+        // (an activation beyond fp16's range -- or a NaN -- sends the next layer to the TF32 kernel, see k_conv64_h)
+        if (big && !(fmaxf(fmaxf(fabsf(acc.x), fabsf(acc.y)), fmaxf(fabsf(acc.z), fabsf(acc.w))) <= CONV_F16_MAX)) *big = 1;
         orow[(size_t)x * 16] = acc;
     }
 }
@@ -104,7 +108,10 @@ __global__ void k_conv_prep_weights(const float *__restrict__ w, float *__restri
 template <bool LAST>
 __global__ void __launch_bounds__(CT_THREADS, 1)
 k_conv64_tc(const __grid_constant__ CtcMaps maps, const float *__restrict__ bias, float *__restrict__ out, int OH, int OW,
-            int ntx, int ntiles) {
+            int ntx, int ntiles, const int *__restrict__ in_big, const int *__restrict__ w_big, int run_if, int *__restrict__ big) {
+    // *in_big | *w_big != 0: this layer's input (or its weights) does not fit fp16 -- the TF32 kernel (run_if = 1) does
+    // the layer, the FP16 kernel (run_if = 0) leaves at once; and the other way round.  in_big == NULL: run.
+    if (in_big && ((*in_big | *w_big) != 0) != (run_if != 0)) return;
     extern __shared__ __align__(1024) unsigned char ctc_raw[];
     CtcSmem &sm = *reinterpret_cast<CtcSmem *>(ctc_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -280,6 +287,7 @@ k_conv64_tc(const __grid_constant__ CtcMaps maps, const float *__restrict__ bias
                 }
                 const float inv = LAST ? 1.0f / sqrtf(fmaxf(ss, 1e-12f)) : 1.0f;   // model.py:64
                 if (y < OH && m < CT_PIX && x < OW) {
+                    float mx = 0.f;                                                 // largest activation written (NaN counts as inf)
                     float *dst = out + ((size_t)y * OW + x) * F;
 #pragma unroll
                     for (int o = 0; o < 32; o += 8) {
@@ -288,6 +296,7 @@ k_conv64_tc(const __grid_constant__ CtcMaps maps, const float *__restrict__ bias
                         for (int k = 0; k < 8; k++) {
                             const float t = __uint_as_float(v0[o + k]);
                             e[k] = LAST ? t * inv : fmaxf(t, 0.f);                  // model.py:120-123
+                            if (!LAST) mx = fmaxf(mx, t != t ? CUDART_INF_F : t);
                         }
                         asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(dst + o), "f"(e[0]), "f"(e[1]),
                                      "f"(e[2]), "f"(e[3]), "f"(e[4]), "f"(e[5]), "f"(e[6]), "f"(e[7])
@@ -300,11 +309,13 @@ k_conv64_tc(const __grid_constant__ CtcMaps maps, const float *__restrict__ bias
                         for (int k = 0; k < 8; k++) {
                             const float t = __uint_as_float(v1[o + k]);
                             e[k] = LAST ? t * inv : fmaxf(t, 0.f);
+                            if (!LAST) mx = fmaxf(mx, t != t ? CUDART_INF_F : t);
                         }
                         asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(dst + 32 + o), "f"(e[0]), "f"(e[1]),
                                      "f"(e[2]), "f"(e[3]), "f"(e[4]), "f"(e[5]), "f"(e[6]), "f"(e[7])
                                      : "memory");
                     }
+                    if (!LAST && big && !(mx <= CONV_F16_MAX)) *big = 1;            // the next layer must not use fp16 operands
                 }
             }
             asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");
@@ -378,11 +389,13 @@ __device__ __forceinline__ void ch_split(const unsigned char *raw, unsigned char
 }
 
 // HWIO [3][3][ic][oc] float32 -> [tap][oc][ic] fp16, hi = fp16(w) and lo = fp16(w - hi)
-__global__ void k_conv_prep_weights_h(const float *__restrict__ w, __half *__restrict__ whi, __half *__restrict__ wlo) {
+__global__ void k_conv_prep_weights_h(const float *__restrict__ w, __half *__restrict__ whi, __half *__restrict__ wlo,
+                                      int *__restrict__ big) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;        // index into [tap][oc][ic]
     if (i >= 9 * F * F) return;
     const int ic = i % F, oc = (i / F) % F, tap = i / (F * F);
     const float x = w[((size_t)tap * F + ic) * F + oc];
+    if (!(fabsf(x) <= CONV_F16_MAX)) *big = 1;                  // this layer's weights do not fit fp16
     const __half h = __float2half_rn(x);
     whi[i] = h;
     wlo[i] = __float2half_rn(x - __half2float(h));
@@ -391,7 +404,10 @@ __global__ void k_conv_prep_weights_h(const float *__restrict__ w, __half *__res
 template <bool LAST>
 __global__ void __launch_bounds__(CT_THREADS, 1)
 k_conv64_h(const __grid_constant__ CtcMaps maps, const float *__restrict__ bias, float *__restrict__ out, int OH, int OW,
-            int ntx, int ntiles) {
+            int ntx, int ntiles, const int *__restrict__ in_big, const int *__restrict__ w_big, int run_if, int *__restrict__ big) {
+    // *in_big | *w_big != 0: this layer's input (or its weights) does not fit fp16 -- the TF32 kernel (run_if = 1) does
+    // the layer, the FP16 kernel (run_if = 0) leaves at once; and the other way round.  in_big == NULL: run.
+    if (in_big && ((*in_big | *w_big) != 0) != (run_if != 0)) return;
     extern __shared__ __align__(1024) unsigned char ctc_raw[];
     ChSmem &sm = *reinterpret_cast<ChSmem *>(ctc_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -563,6 +579,7 @@ k_conv64_h(const __grid_constant__ CtcMaps maps, const float *__restrict__ bias,
                 }
                 const float inv = LAST ? 1.0f / sqrtf(fmaxf(ss, 1e-12f)) : 1.0f;   // model.py:64
                 if (y < OH && m < CT_PIX && x < OW) {
+                    float mx = 0.f;                                                 // largest activation written (NaN counts as inf)
                     float *dst = out + ((size_t)y * OW + x) * F;
 #pragma unroll
                     for (int o = 0; o < 32; o += 8) {
@@ -571,6 +588,7 @@ k_conv64_h(const __grid_constant__ CtcMaps maps, const float *__restrict__ bias,
                         for (int k = 0; k < 8; k++) {
                             const float t = __uint_as_float(v0[o + k]);
                             e[k] = LAST ? t * inv : fmaxf(t, 0.f);                  // model.py:120-123
+                            if (!LAST) mx = fmaxf(mx, t != t ? CUDART_INF_F : t);
                         }
                         asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(dst + o), "f"(e[0]), "f"(e[1]),
                                      "f"(e[2]), "f"(e[3]), "f"(e[4]), "f"(e[5]), "f"(e[6]), "f"(e[7])
@@ -583,11 +601,13 @@ k_conv64_h(const __grid_constant__ CtcMaps maps, const float *__restrict__ bias,
                         for (int k = 0; k < 8; k++) {
                             const float t = __uint_as_float(v1[o + k]);
                             e[k] = LAST ? t * inv : fmaxf(t, 0.f);
+                            if (!LAST) mx = fmaxf(mx, t != t ? CUDART_INF_F : t);
                         }
                         asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(dst + 32 + o), "f"(e[0]), "f"(e[1]),
                                      "f"(e[2]), "f"(e[3]), "f"(e[4]), "f"(e[5]), "f"(e[6]), "f"(e[7])
                                      : "memory");
                     }
+                    if (!LAST && big && !(mx <= CONV_F16_MAX)) *big = 1;            // the next layer must not use fp16 operands
                 }
             }
             asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");
@@ -622,39 +642,51 @@ using namespace mccnn;
 
 extern "C" {
 
-// operand format of layers 2..n: fp16 hi/lo (default) or the TF32 split (MCCNN_CONV_TF32=1: networks whose activations
-// leave fp16's range); read once, mccnn_features_prepare and the forward calls must agree
+// Layers 2..n run with FP16 hi/lo operands (k_conv64_h) unless the layer's input or weights leave fp16's range, in which
+// case the TF32 kernel (k_conv64_tc) does that layer: both kernels are launched for every layer and exactly one of them
+// works, decided on the device by two flags -- gate[0]: the producer of the layer's input saw an activation beyond
+// CONV_F16_MAX (set by its epilogue), gate[1]: the weight split did.  No host read-back.  MCCNN_CONV_TF32=1 forces the
+// TF32 kernel everywhere (only it is launched).
 static bool conv_tf32() {
     static int v = -1;
     if (v < 0) { const char *e = getenv("MCCNN_CONV_TF32"); v = (e && atoi(e) != 0) ? 1 : 0; }
     return v == 1;
 }
 
-static size_t conv_weights_floats(int num_layers) { return (size_t)(num_layers > 1 ? num_layers - 1 : 0) * 2 * 9 * F * F; }
+// prepared weights of layer l >= 1 (floats): [tf32 hi | tf32 lo | fp16 hi, fp16 lo (halves) | flag word + padding]
+constexpr size_t CONV_PREP_FLOATS = 3 * 9 * F * F + 16;
+static size_t conv_weights_floats(int num_layers) { return (size_t)(num_layers > 1 ? num_layers - 1 : 0) * CONV_PREP_FLOATS; }
+constexpr size_t CONV_FLAG_INTS = 32;          // per call: flag of every layer's input (in the activation scratch)
 
 size_t mccnn_features_scratch_bytes(int H, int W, int pad, int num_layers) {
     if (H < 1 || W < 1 || num_layers < 1 || pad < 0 || H + 2 * pad < 3 || W + 2 * pad < 3) return 0;
     size_t oh = (size_t)H + 2 * pad - 2, ow = (size_t)W + 2 * pad - 2;
-    // two ping-pong activation maps + the pre-split weights of layers 2..n
-    return (2 * oh * ow * F + conv_weights_floats(num_layers)) * sizeof(float);
+    // two ping-pong activation maps + the per-layer range flags + the pre-split weights of layers 2..n
+    return (2 * oh * ow * F + CONV_FLAG_INTS + conv_weights_floats(num_layers)) * sizeof(float);
 }
 
 size_t mccnn_features_weights_bytes(int num_layers) {
     return num_layers >= 1 ? conv_weights_floats(num_layers) * sizeof(float) : 0;
 }
 
+static int prep_layer(const float *w, float *base, cudaStream_t s) {
+    float *whi = base, *wlo = base + 9 * F * F;
+    __half *hhi = reinterpret_cast<__half *>(base + 2 * 9 * F * F);
+    int *wflag = reinterpret_cast<int *>(base + 3 * 9 * F * F);
+    MCCNN_CUDA(cudaMemsetAsync(wflag, 0, 16 * sizeof(float), s));
+    k_conv_prep_weights<<<cdiv(9 * F * F, 256), 256, 0, s>>>(w, whi, wlo);
+    MCCNN_LAUNCHED("conv_prep_weights");
+    k_conv_prep_weights_h<<<cdiv(9 * F * F, 256), 256, 0, s>>>(w, hhi, hhi + 9 * F * F, wflag);
+    MCCNN_LAUNCHED("conv_prep_weights_h");
+    return MCCNN_OK;
+}
+
 int mccnn_features_prepare(int num_layers, const float *const *weights_host, void *prepared, void *stream) {
     MCCNN_REQUIRE(weights_host && num_layers >= 1 && num_layers <= 16, "features_prepare: bad arguments");
     MCCNN_REQUIRE(num_layers == 1 || (prepared && ((uintptr_t)prepared & 31) == 0), "features_prepare: prepared must be 32-byte aligned");
     for (int l = 1; l < num_layers; l++) {
-        float *whi = (float *)prepared + (size_t)(l - 1) * 2 * 9 * F * F, *wlo = whi + 9 * F * F;
-        if (conv_tf32()) {
-            k_conv_prep_weights<<<cdiv(9 * F * F, 256), 256, 0, (cudaStream_t)stream>>>(weights_host[l], whi, wlo);
-        } else {
-            __half *hhi = reinterpret_cast<__half *>(whi);
-            k_conv_prep_weights_h<<<cdiv(9 * F * F, 256), 256, 0, (cudaStream_t)stream>>>(weights_host[l], hhi, hhi + 9 * F * F);
-        }
-        MCCNN_LAUNCHED("conv_prep_weights");
+        int rc = prep_layer(weights_host[l], (float *)prepared + (size_t)(l - 1) * CONV_PREP_FLOATS, (cudaStream_t)stream);
+        if (rc) return rc;
     }
     return MCCNN_OK;
 }
@@ -673,13 +705,15 @@ static int features_impl(const float *img, int H, int W, int pad, int num_layers
     float *buf[2];
     buf[0] = (float *)scratch;
     buf[1] = buf[0] ? buf[0] + (size_t)oh * ow * F : nullptr;
+    int *flags = buf[0] ? reinterpret_cast<int *>(buf[1] + (size_t)oh * ow * F) : nullptr;   // flags[l]: input of layer l too big
     // the pre-split weights of layers 2..n: the caller's (mccnn_features_prepare, once per network), else made here
-    float *wsplit = prepared ? const_cast<float *>(prepared) : (buf[0] ? buf[1] + (size_t)oh * ow * F : nullptr);
+    float *wsplit = prepared ? const_cast<float *>(prepared) : (buf[0] ? reinterpret_cast<float *>(flags + CONV_FLAG_INTS) : nullptr);
     float *dst = (num_layers == 1) ? out : buf[0];
+    if (flags) MCCNN_CUDA(cudaMemsetAsync(flags, 0, CONV_FLAG_INTS * sizeof(int), s));
     {
         MCCNN_REQUIRE(oh <= 65535, "features: image too tall (%d rows)", oh);
         k_conv1<<<dim3(cdiv(ow, 16 * C1_PX), oh), 256, 0, s>>>(img, weights_host[0], biases_host[0], dst, H, W, pad, oh, ow,
-                                                                        num_layers > 1);
+                                                                        num_layers > 1, num_layers > 1 ? flags + 1 : nullptr);
         MCCNN_LAUNCHED("conv1");
     }
     if (num_layers == 1) {
@@ -697,39 +731,45 @@ static int features_impl(const float *img, int H, int W, int pad, int num_layers
     MCCNN_CUDA(cudaFuncSetAttribute(k_conv64_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CtcSmem)));
     MCCNN_CUDA(cudaFuncSetAttribute(k_conv64_h<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ChSmem)));
     MCCNN_CUDA(cudaFuncSetAttribute(k_conv64_h<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ChSmem)));
-    const bool tf32 = conv_tf32();
+    const bool force_tf32 = conv_tf32();
     const float *src = dst;
     int ih = oh, iw = ow;
     for (int l = 1; l < num_layers; l++) {
         oh = ih - 2; ow = iw - 2;
         const bool last = (l == num_layers - 1);
         float *d = last ? out : buf[l & 1];
-        float *whi = wsplit + (size_t)(l - 1) * 2 * 9 * F * F, *wlo = whi + 9 * F * F;
-        __half *hhi = reinterpret_cast<__half *>(whi), *hlo = hhi + 9 * F * F;
+        float *base = wsplit + (size_t)(l - 1) * CONV_PREP_FLOATS;
+        float *whi = base, *wlo = base + 9 * F * F;
+        __half *hhi = reinterpret_cast<__half *>(base + 2 * 9 * F * F), *hlo = hhi + 9 * F * F;
+        int *wflag = reinterpret_cast<int *>(base + 3 * 9 * F * F);
         if (!prepared) {
-            if (tf32) k_conv_prep_weights<<<cdiv(9 * F * F, 256), 256, 0, s>>>(weights_host[l], whi, wlo);
-            else k_conv_prep_weights_h<<<cdiv(9 * F * F, 256), 256, 0, s>>>(weights_host[l], hhi, hlo);
-            MCCNN_LAUNCHED("conv_prep_weights");
+            int rc = prep_layer(weights_host[l], base, s);
+            if (rc) return rc;
         }
-        CtcMaps maps;
-        int rc = tc_encode_map_3d(maps.in, src, F, iw, ih, 32, 128, true, "features");
-        if (rc) return rc;
-        rc = tf32 ? tc_encode_map_3d(maps.whi, whi, F, F, 9, 32, F, true, "features")
-                  : tc_encode_map_3d_f16_sw64(maps.whi, hhi, F, F, 9, 32, F, "features");
-        if (rc) return rc;
-        rc = tf32 ? tc_encode_map_3d(maps.wlo, wlo, F, F, 9, 32, F, true, "features")
-                  : tc_encode_map_3d_f16_sw64(maps.wlo, hlo, F, F, 9, 32, F, "features");
-        if (rc) return rc;
+        const int *in_big = flags + l;                            // set by the producer of this layer's input
+        int *big = last ? nullptr : flags + l + 1;
         const int ntx = cdiv(ow, CT_PIX), nty = cdiv(oh, CT_ROWS);
         const int ntiles = ntx * nty;
         const int grid = ntiles < num_sms ? ntiles : num_sms;
-        if (tf32) {
-            if (last) k_conv64_tc<true><<<grid, CT_THREADS, sizeof(CtcSmem), s>>>(maps, biases_host[l], d, oh, ow, ntx, ntiles);
-            else k_conv64_tc<false><<<grid, CT_THREADS, sizeof(CtcSmem), s>>>(maps, biases_host[l], d, oh, ow, ntx, ntiles);
-        } else {
-            if (last) k_conv64_h<true><<<grid, CT_THREADS, sizeof(ChSmem), s>>>(maps, biases_host[l], d, oh, ow, ntx, ntiles);
-            else k_conv64_h<false><<<grid, CT_THREADS, sizeof(ChSmem), s>>>(maps, biases_host[l], d, oh, ow, ntx, ntiles);
+        CtcMaps maps;
+        int rc = tc_encode_map_3d(maps.in, src, F, iw, ih, 32, 128, true, "features");
+        if (rc) return rc;
+        if (!force_tf32) {
+            rc = tc_encode_map_3d_f16_sw64(maps.whi, hhi, F, F, 9, 32, F, "features");
+            if (rc) return rc;
+            rc = tc_encode_map_3d_f16_sw64(maps.wlo, hlo, F, F, 9, 32, F, "features");
+            if (rc) return rc;
+            if (last) k_conv64_h<true><<<grid, CT_THREADS, sizeof(ChSmem), s>>>(maps, biases_host[l], d, oh, ow, ntx, ntiles, in_big, wflag, 0, big);
+            else k_conv64_h<false><<<grid, CT_THREADS, sizeof(ChSmem), s>>>(maps, biases_host[l], d, oh, ow, ntx, ntiles, in_big, wflag, 0, big);
+            MCCNN_LAUNCHED("conv64_h");
         }
+        rc = tc_encode_map_3d(maps.whi, whi, F, F, 9, 32, F, true, "features");
+        if (rc) return rc;
+        rc = tc_encode_map_3d(maps.wlo, wlo, F, F, 9, 32, F, true, "features");
+        if (rc) return rc;
+        const int *tgate = force_tf32 ? nullptr : in_big;
+        if (last) k_conv64_tc<true><<<grid, CT_THREADS, sizeof(CtcSmem), s>>>(maps, biases_host[l], d, oh, ow, ntx, ntiles, tgate, wflag, 1, big);
+        else k_conv64_tc<false><<<grid, CT_THREADS, sizeof(CtcSmem), s>>>(maps, biases_host[l], d, oh, ow, ntx, ntiles, tgate, wflag, 1, big);
         MCCNN_LAUNCHED("conv64_tc");
         src = d; ih = oh; iw = ow;
     }

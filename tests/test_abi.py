@@ -53,8 +53,9 @@ def test_no_compute_calls_without_gpu_but_pure_queries_work(pkg):
     assert lib.mccnn_abi_version() == 2
     for D in (1, 2, 3, 4, 11, 192, 400):
         assert lib.mccnn_dpitch(D) == pkg._ffi.dpitch(D) == (D + 3) // 4 * 4
-    # two ping-pong activation maps + the hi/lo split weights of layers 2..5
-    assert lib.mccnn_features_scratch_bytes(128, 128, 5, 5) == (2 * 136 * 136 * 64 + 4 * 2 * 9 * 64 * 64) * 4
+    # two ping-pong activation maps + 32 range flags + per layer 2..5 the TF32 hi/lo split, the FP16 hi/lo split and a flag block
+    assert lib.mccnn_features_scratch_bytes(128, 128, 5, 5) == (2 * 136 * 136 * 64 + 32 + 4 * (3 * 9 * 64 * 64 + 16)) * 4
+    assert lib.mccnn_features_weights_bytes(5) == 4 * (3 * 9 * 64 * 64 + 16) * 4
     assert lib.mccnn_sgm_scratch_bytes(16, 40, 8) > 0
     # argument validation happens before any CUDA call and reports through the error string
     rc = lib.mccnn_cost_volume(None, None, None, None, 4, 4, 64, 8, None)

@@ -107,6 +107,22 @@ def test_features_with_prepared_weights_are_the_bits_of_the_plain_call(pf):
     assert torch.equal(a, b)
 
 
+def test_features_outside_the_fp16_range_take_the_tf32_kernel(pf, oracle, checkpoint_golden):
+    """The tensor-core layers use FP16 hi/lo operands unless a layer's input or weights exceed fp16's range (65504): then the
+    device-side gate sends that layer to the TF32 kernel.  Activations of 1e6 (first-layer weights scaled), weights of 1e5
+    (third layer scaled), and both: the normalised features still match the float32 C oracle."""
+    ws, bs = checkpoint_golden
+    rng = np.random.default_rng(3)
+    img = rng.standard_normal((40, 150)).astype(np.float32)
+    for name, scale in (("activations", {0: 1e6}), ("weights", {2: 1e5}), ("both", {0: 3e5, 3: 2e5})):
+        w2 = [w * np.float32(scale.get(i, 1.0)) for i, w in enumerate(ws)]
+        b2 = [b * np.float32(np.prod([scale.get(j, 1.0) for j in range(i + 1)])) for i, b in enumerate(bs)]
+        f, _ = pf.compute_features(img[..., None], img[..., None], 11, 11, (w2, b2))
+        ref = oracle.net_forward(img, w2, b2)
+        assert np.isfinite(f).all(), name
+        np.testing.assert_allclose(f, ref, atol=FEAT_ATOL, rtol=0, err_msg=name)
+
+
 def test_features_of_a_row_band_are_the_bits_of_the_whole_image(pf):
     """The net is local (11x11 receptive field), so rows [lo, hi) of the features need image rows [lo-5, hi+5) only --
     what the row-band feature exchange of the slab partition relies on.  The tensor-core layers must also give the SAME
