@@ -30,6 +30,7 @@ __global__ void __launch_bounds__(256) k_conv1(const float *__restrict__ img, co
     for (int t = 0; t < 9; t++) wv[t] = *reinterpret_cast<const float4 *>(wgt + t * F + oc);
     const float4 bv = *reinterpret_cast<const float4 *>(bias + oc);
     float4 *orow = reinterpret_cast<float4 *>(out) + (size_t)y * OW * 16 + (oc >> 2);
+    unsigned mxb = 0;
 #pragma unroll 2
     for (int it = 0; it < C1_PX; it++) {
         const int x = (blockIdx.x * C1_PX + it) * 16 + slot;
@@ -47,10 +48,12 @@ __global__ void __launch_bounds__(256) k_conv1(const float *__restrict__ img, co
             }
         float4 acc = make_float4(bv.x + sum.x, bv.y + sum.y, bv.z + sum.z, bv.w + sum.w);
         if (relu) { acc.x = fmaxf(acc.x, 0.f); acc.y = fmaxf(acc.y, 0.f); acc.z = fmaxf(acc.z, 0.f); acc.w = fmaxf(acc.w, 0.f); }
-        // (an activation beyond fp16's range -- or a NaN -- sends the next layer to the TF32 kernel, see k_conv64_h)
-        if (big && !(fmaxf(fmaxf(fabsf(acc.x), fabsf(acc.y)), fmaxf(fabsf(acc.z), fabsf(acc.w))) <= CONV_F16_MAX)) *big = 1;
+        // (the largest activation written, as bits: after the ReLU they are non-negative, so unsigned order = float order)
+        mxb = max(max(mxb, __float_as_uint(acc.x)), max(__float_as_uint(acc.y), max(__float_as_uint(acc.z), __float_as_uint(acc.w))));
         orow[(size_t)x * 16] = acc;
     }
+    // an activation beyond fp16's range sends the next layer to the TF32 kernel (see k_conv64_h); only asked for with the ReLU
+    if (big && relu && mxb > __float_as_uint(CONV_F16_MAX)) *big = 1;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -287,7 +290,7 @@ k_conv64_tc(const __grid_constant__ CtcMaps maps, const float *__restrict__ bias
                 }
                 const float inv = LAST ? 1.0f / sqrtf(fmaxf(ss, 1e-12f)) : 1.0f;   // model.py:64
                 if (y < OH && m < CT_PIX && x < OW) {
-                    float mx = 0.f;                                                 // largest activation written (NaN counts as inf)
+                    unsigned mxb = 0;                                               // largest activation written, as bits
                     float *dst = out + ((size_t)y * OW + x) * F;
 #pragma unroll
                     for (int o = 0; o < 32; o += 8) {
@@ -296,7 +299,7 @@ k_conv64_tc(const __grid_constant__ CtcMaps maps, const float *__restrict__ bias
                         for (int k = 0; k < 8; k++) {
                             const float t = __uint_as_float(v0[o + k]);
                             e[k] = LAST ? t * inv : fmaxf(t, 0.f);                  // model.py:120-123
-                            if (!LAST) mx = fmaxf(mx, t != t ? CUDART_INF_F : t);
+                            if (!LAST) mxb = max(mxb, __float_as_uint(e[k]));   // (non-negative after the ReLU)
                         }
                         asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(dst + o), "f"(e[0]), "f"(e[1]),
                                      "f"(e[2]), "f"(e[3]), "f"(e[4]), "f"(e[5]), "f"(e[6]), "f"(e[7])
@@ -309,13 +312,13 @@ k_conv64_tc(const __grid_constant__ CtcMaps maps, const float *__restrict__ bias
                         for (int k = 0; k < 8; k++) {
                             const float t = __uint_as_float(v1[o + k]);
                             e[k] = LAST ? t * inv : fmaxf(t, 0.f);
-                            if (!LAST) mx = fmaxf(mx, t != t ? CUDART_INF_F : t);
+                            if (!LAST) mxb = max(mxb, __float_as_uint(e[k]));   // (non-negative after the ReLU)
                         }
                         asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(dst + 32 + o), "f"(e[0]), "f"(e[1]),
                                      "f"(e[2]), "f"(e[3]), "f"(e[4]), "f"(e[5]), "f"(e[6]), "f"(e[7])
                                      : "memory");
                     }
-                    if (!LAST && big && !(mx <= CONV_F16_MAX)) *big = 1;            // the next layer must not use fp16 operands
+                    if (!LAST && big && mxb > __float_as_uint(CONV_F16_MAX)) *big = 1;   // the next layer must not use fp16 operands
                 }
             }
             asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");
@@ -579,7 +582,7 @@ k_conv64_h(const __grid_constant__ CtcMaps maps, const float *__restrict__ bias,
                 }
                 const float inv = LAST ? 1.0f / sqrtf(fmaxf(ss, 1e-12f)) : 1.0f;   // model.py:64
                 if (y < OH && m < CT_PIX && x < OW) {
-                    float mx = 0.f;                                                 // largest activation written (NaN counts as inf)
+                    unsigned mxb = 0;                                               // largest activation written, as bits
                     float *dst = out + ((size_t)y * OW + x) * F;
 #pragma unroll
                     for (int o = 0; o < 32; o += 8) {
@@ -588,7 +591,7 @@ k_conv64_h(const __grid_constant__ CtcMaps maps, const float *__restrict__ bias,
                         for (int k = 0; k < 8; k++) {
                             const float t = __uint_as_float(v0[o + k]);
                             e[k] = LAST ? t * inv : fmaxf(t, 0.f);                  // model.py:120-123
-                            if (!LAST) mx = fmaxf(mx, t != t ? CUDART_INF_F : t);
+                            if (!LAST) mxb = max(mxb, __float_as_uint(e[k]));   // (non-negative after the ReLU)
                         }
                         asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(dst + o), "f"(e[0]), "f"(e[1]),
                                      "f"(e[2]), "f"(e[3]), "f"(e[4]), "f"(e[5]), "f"(e[6]), "f"(e[7])
@@ -601,13 +604,13 @@ k_conv64_h(const __grid_constant__ CtcMaps maps, const float *__restrict__ bias,
                         for (int k = 0; k < 8; k++) {
                             const float t = __uint_as_float(v1[o + k]);
                             e[k] = LAST ? t * inv : fmaxf(t, 0.f);
-                            if (!LAST) mx = fmaxf(mx, t != t ? CUDART_INF_F : t);
+                            if (!LAST) mxb = max(mxb, __float_as_uint(e[k]));   // (non-negative after the ReLU)
                         }
                         asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(dst + 32 + o), "f"(e[0]), "f"(e[1]),
                                      "f"(e[2]), "f"(e[3]), "f"(e[4]), "f"(e[5]), "f"(e[6]), "f"(e[7])
                                      : "memory");
                     }
-                    if (!LAST && big && !(mx <= CONV_F16_MAX)) *big = 1;            // the next layer must not use fp16 operands
+                    if (!LAST && big && mxb > __float_as_uint(CONV_F16_MAX)) *big = 1;   // the next layer must not use fp16 operands
                 }
             }
             asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");
