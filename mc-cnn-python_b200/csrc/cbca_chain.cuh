@@ -4,7 +4,8 @@
 // (pf:640-650, :157-161).  As two streaming passes (cbca_stream.cuh) a round moves 16 B per cell through HBM: Hs_k out
 // and back, out_k out and back.  k_cbca_colrow_g runs the column pass of round k and the row pass of round k+1 as ONE
 // kernel with out_k in shared memory only:
-//     Hs_k -> [out_k] -> Hs_{k+1},   8 B per cell per round;   a call of n rounds is  rows | (n-1) x colrow | cols.
+//     Hs_k -> [out_k] -> Hs_{k+1},   8 B per cell per round;   a call of n rounds is  rows | (n-1) x colrow | close
+// (rows = k_cbca_pass<rows>, close = k_cbca_close_g below: the last column pass in the same style).
 // Fusing this way needs no vertical on-chip state (fusing the two passes of one round needs up to 27 row sums per
 // column on chip).
 //
@@ -25,6 +26,11 @@
 // per 4 * GPT cells and the GPT accumulators are independent chains, so a warp needs fewer instructions per cell and
 // stalls less per instruction; the price is GPT times the shared-memory tile.  GPT = 3 is the whole disparity row at
 // ndisp 192.  Same additions in the same order as the two-pass form => bit-identical to it (tests: *_match_two_pass).
+// L2 look-ahead: rows h-1 and h of a box were fetched by the CTAs of the rows above, row h+1 is first touched by this
+// CTA; each CTA asks L2 (cp.async.bulk.prefetch.tensor) for the row that the CTA `ahead` rows below will be first to touch.
+// Settled pixels: a pixel whose four arms are zero is its own region (out_k = Hs_k = out_{k-1} in every round); from the
+// third pass over the volume on both ping-pong buffers hold its value, so it gets no work and no store, and the pixels
+// that do have work are compacted into a list.
 #pragma once
 #include "cbca_stream.cuh"
 #include "tc_common.cuh"
